@@ -44,7 +44,7 @@ constexpr int kBK = 64;          // k-block: 64 elements = 128 B of 16-bit X per
 constexpr int kTileN = 128;      // output features per CTA (TMEM lanes)
 constexpr int kDecodeWarps = 8;
 constexpr int kThreads = 32 * (2 + kDecodeWarps);
-constexpr int kPrefetch = 2;     // decode-side global prefetch distance (k-blocks)
+constexpr int kPrefetch = 4;     // decode-side global prefetch distance (k-blocks of one warp set)
 
 struct Gemm4Params {
     const uint8_t* B;            // packed codes [N, K/2]
@@ -88,6 +88,49 @@ struct ScaleSrc {
 // rounds the product and the sum separately.  We follow the second (mul, then add), so the
 // fused GEMM sees exactly the weights F.dequantize_4bit returns.
 
+
+// ---------------------------------------------------------------- register-resident decode
+// W_T = rn_T(value(code) * scale) takes only 16 distinct values per quantisation block, so a
+// decode thread first builds that 16-entry table (16 fp32 multiplies by immediates, 8 packed
+// roundings -- bit-identical to rounding every element) and keeps it in 8 registers as two
+// byte planes (low bytes / high bytes of the 16-bit entries).  Codes are then translated with
+// PRMT (byte permute) only: no shared-memory look-up table, hence no bank conflicts and no
+// competition with the tensor core for shared-memory bandwidth.
+struct DecodeTable {
+    uint32_t lo[4];  // lo[j] = low bytes of entries 4j .. 4j+3
+    uint32_t hi[4];  // hi[j] = high bytes
+};
+
+template <typename T, int QT> __device__ __forceinline__ void build_table(float scale, DecodeTable& t) {
+    uint32_t pr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        pr[j] = pack2<T>(mul_ftz(code4_value<QT>(2 * j), scale), mul_ftz(code4_value<QT>(2 * j + 1), scale));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        t.lo[j] = __byte_perm(pr[2 * j], pr[2 * j + 1], 0x6420);
+        t.hi[j] = __byte_perm(pr[2 * j], pr[2 * j + 1], 0x7531);
+    }
+}
+
+// One packed word = 4 bytes = 8 codes (byte b: element 2b in the high nibble) -> 4 registers of
+// T pairs, element 2b in the low half.  Selector nibbles must stay < 8 (bit 3 is PRMT's
+// sign-replicate flag): `c` carries code & 7, `selm` picks between the idx<8 / idx>=8 halves.
+__device__ __forceinline__ void decode_word(uint32_t w, const DecodeTable& t, uint32_t* o) {
+    const uint32_t c7 = w & 0x77777777u;
+    const uint32_t w1 = w >> 1;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const uint32_t c = g ? (c7 >> 16) : c7;
+        const uint32_t m = g ? (w1 >> 16) : w1;
+        const uint32_t selm = (m & 0x4444u) | 0x3210u;
+        const uint32_t lo = __byte_perm(__byte_perm(t.lo[0], t.lo[1], c), __byte_perm(t.lo[2], t.lo[3], c), selm);
+        const uint32_t hi = __byte_perm(__byte_perm(t.hi[0], t.hi[1], c), __byte_perm(t.hi[2], t.hi[3], c), selm);
+        o[2 * g] = __byte_perm(lo, hi, 0x4051);      // (T[hi nibble of byte 0], T[lo nibble of byte 0])
+        o[2 * g + 1] = __byte_perm(lo, hi, 0x6273);  // byte 1
+    }
+}
+
 template <typename T, int QT, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Gemm4Params p) {
@@ -97,10 +140,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kXStageBytes = MT * 128;
     uint8_t* sx = smem;
-    float2* lut2 = reinterpret_cast<float2*>(smem + kStages * kXStageBytes);  // 256 x 8 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kXStageBytes + 2048);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kXStageBytes);
     uint64_t* full_x = bars;                  // [kStages] TMA -> MMA
-    uint64_t* full_w = bars + kStages;        // [kStages] decode -> MMA   (count = kDecodeWarps)
+    uint64_t* full_w = bars + kStages;        // [kStages] decode -> MMA   (count = kDecodeWarps / 2)
     uint64_t* empty = bars + 2 * kStages;     // [kStages] MMA -> TMA + decode (tcgen05.commit)
     uint64_t* acc_full = bars + 3 * kStages;  // MMA -> epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
@@ -125,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::prefetch_tmap(&tmap_x);
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(&full_x[s], 1);
-            ptx::mbar_init(&full_w[s], kDecodeWarps);
+            ptx::mbar_init(&full_w[s], kDecodeWarps / 2);
             ptx::mbar_init(&empty[s], 1);
         }
         ptx::mbar_init(acc_full, 1);
@@ -134,9 +176,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 1) {
         ptx::tmem_alloc<kTmemCols>(tmem_slot);
         ptx::tmem_relinquish();
-    }
-    if (threadIdx.x < 256) {
-        lut2[threadIdx.x] = make_float2(code4_value<QT>(threadIdx.x >> 4), code4_value<QT>(threadIdx.x & 15u));
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -188,73 +227,82 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ================================================================== decode warps
         const int dw = warp - 2;          // 0..7
         const int quarter = warp & 3;     // TMEM lane quarter this warp may touch
-        const int khalf = dw >> 2;        // which 32 of the 64 k's
+        const int par = dw >> 2;          // warp set: handles k-blocks i with (i & 1) == par
+        const int khalf = par;            // epilogue: which half of the accumulator columns
         const int row = quarter * 32 + lane;
         const int n = n0 + row;
         const bool n_ok = n < p.N;
-        const uint8_t* wrow = p.B + ((long long)(n_ok ? n : 0) * p.K >> 1) + khalf * 16;
-        const long long e_row = (long long)(n_ok ? n : 0) * p.K + khalf * 32;
+        const uint8_t* wrow = p.B + ((long long)(n_ok ? n : 0) * p.K >> 1);
+        const long long e_row = (long long)(n_ok ? n : 0) * p.K;
         ScaleSrc sc{p.absmax, p.absmax_8bit, p.absmax_code, p.absmax_offset ? __ldg(p.absmax_offset) : 0.0f};
+        const bool two_scales = p.log2_bs == 5;  // blocksize 32: two quantisation blocks per 64-wide k-block
 
-        uint4 wq[kPrefetch];
-        float wsc[kPrefetch];
+        // This warp set's k-blocks: i = 2 t + par, t = 0 .. cnt-1.
+        const int cnt = (nkb - par + 1) >> 1;
+
+        // Register prefetch ring, kPrefetch of this warp set's k-blocks deep.  The loop is unrolled
+        // by kPrefetch so that slot j is a fixed set of registers: no register rotation (a move out
+        // of a load's destination would wait for the load and collapse the prefetch).
+        uint4 wq[kPrefetch][2];
+        float wsc[kPrefetch][2];
 #pragma unroll
         for (int j = 0; j < kPrefetch; ++j) {
-            wq[j] = make_uint4(0, 0, 0, 0);
-            wsc[j] = 0.f;
-            if (j < nkb && n_ok) {
-                const int kb = kb_begin + j;
-                wq[j] = __ldg(reinterpret_cast<const uint4*>(wrow + (long long)kb * (kBK / 2)));
-                wsc[j] = sc.load((e_row + (long long)kb * kBK) >> p.log2_bs);
+            wq[j][0] = wq[j][1] = make_uint4(0, 0, 0, 0);
+            wsc[j][0] = wsc[j][1] = 0.f;
+            if (j < cnt && n_ok) {
+                const int kb = kb_begin + 2 * j + par;
+                const uint8_t* src = wrow + (long long)kb * (kBK / 2);
+                wq[j][0] = ldg_stream_v4(src);
+                wq[j][1] = ldg_stream_v4(src + 16);
+                const long long e = e_row + (long long)kb * kBK;
+                wsc[j][0] = sc.load(e >> p.log2_bs);
+                if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
             }
         }
 
-        int s = 0;
-        uint32_t ph = 0;
-        for (int i = 0; i < nkb; ++i) {
-            // current k-block's codes and scale (registers rotate: static indexing only)
-            const uint4 q = wq[0];
-            const float scale = wsc[0];
+        for (int t0 = 0; t0 < cnt; t0 += kPrefetch) {
 #pragma unroll
-            for (int j = 0; j + 1 < kPrefetch; ++j) {
-                wq[j] = wq[j + 1];
-                wsc[j] = wsc[j + 1];
-            }
-            {
-                const int nxt = i + kPrefetch;
-                wq[kPrefetch - 1] = make_uint4(0, 0, 0, 0);
-                wsc[kPrefetch - 1] = 0.f;
-                if (nxt < nkb && n_ok) {
-                    const int kb = kb_begin + nxt;
-                    wq[kPrefetch - 1] = __ldg(reinterpret_cast<const uint4*>(wrow + (long long)kb * (kBK / 2)));
-                    wsc[kPrefetch - 1] = sc.load((e_row + (long long)kb * kBK) >> p.log2_bs);
-                }
-            }
+            for (int j = 0; j < kPrefetch; ++j) {
+                const int t = t0 + j;
+                if (t < cnt) {
+                    const int i = 2 * t + par;
+                    const int s = i & (kStages - 1);
+                    const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+                    const uint4 q0 = wq[j][0], q1 = wq[j][1];
+                    const float sc0 = wsc[j][0], sc1 = wsc[j][1];
+                    if (t + kPrefetch < cnt && n_ok) {
+                        const int kb = kb_begin + 2 * (t + kPrefetch) + par;
+                        const uint8_t* src = wrow + (long long)kb * (kBK / 2);
+                        wq[j][0] = ldg_stream_v4(src);
+                        wq[j][1] = ldg_stream_v4(src + 16);
+                        const long long e = e_row + (long long)kb * kBK;
+                        wsc[j][0] = sc.load(e >> p.log2_bs);
+                        if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
+                    }
 
-            // decode 32 codes -> 16 packed T pairs (element 2b = high nibble -> low half)
-            uint32_t r[16];
-            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t byte = (qw[w] >> (8 * b)) & 0xffu;
-                    const float2 c = lut2[byte];
-                    r[4 * w + b] = pack2<T>(mul_ftz(c.x, scale), mul_ftz(c.y, scale));
-                }
-            }
+                    // 64 codes of row n -> 32 registers of T pairs
+                    uint32_t r[32];
+                    DecodeTable tab;
+                    build_table<T, QT>(sc0, tab);
+                    decode_word(q0.x, tab, r + 0);
+                    decode_word(q0.y, tab, r + 4);
+                    decode_word(q0.z, tab, r + 8);
+                    decode_word(q0.w, tab, r + 12);
+                    if (two_scales) build_table<T, QT>(sc1, tab);
+                    decode_word(q1.x, tab, r + 16);
+                    decode_word(q1.y, tab, r + 20);
+                    decode_word(q1.z, tab, r + 24);
+                    decode_word(q1.w, tab, r + 28);
 
-            ptx::mbar_wait(&empty[s], ph ^ 1u);  // the MMAs that read this TMEM stage have retired
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 32 + khalf * 16;
-            ptx::tmem_st_x16(taddr, r);
-            ptx::tmem_wait_st();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&full_w[s]);
-            if (++s == kStages) {
-                s = 0;
-                ph ^= 1u;
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);  // the MMAs that read this TMEM stage have retired
+                    ptx::tc_fence_after();
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 32;
+                    ptx::tmem_st_x32(taddr, r);
+                    ptx::tmem_wait_st();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&full_w[s]);
+                }
             }
         }
 
@@ -429,7 +477,7 @@ Workspace* get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_cou
 
 template <typename T, int QT, int MT>
 bool launch_mt(const CUtensorMap& tmap, Gemm4Params& p, cudaStream_t stream) {
-    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(kStages) * MT * 128 + 2048 /*lut*/ + 256 /*barriers*/;
+    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(kStages) * MT * 128 + 256 /*barriers*/;
     static bool attr_set = false;
     auto kern = gemm4_tc_kernel<T, QT, MT>;
     if (!attr_set) {
@@ -447,8 +495,9 @@ bool launch_mt(const CUtensorMap& tmap, Gemm4Params& p, cudaStream_t stream) {
     const int sms = device_sm_count();
     int splits = 1;
     const int tiles = n_tiles * m_tiles;
-    if (tiles < sms) {
-        splits = (sms + tiles - 1) / tiles;
+    if (tiles * 2 <= sms) {
+        // one wave: the largest split count whose grid still fits the machine
+        splits = sms / tiles;
         int max_by_k = p.kblocks_total / 4;
         if (max_by_k < 1) max_by_k = 1;
         if (splits > max_by_k) splits = max_by_k;

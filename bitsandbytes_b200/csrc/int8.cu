@@ -326,12 +326,23 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 uint32_t w[16];
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
-                    const float f0 = dequant_value((int)v[t], sca, s_scb[c + t], s_bias[c + t]);
-                    const float f1 = dequant_value((int)v[t + 1], sca, s_scb[c + t + 1], s_bias[c + t + 1]);
-                    if (EPI == 1)
+                    if (EPI == 1) {
+                        const float f0 = dequant_value((int)v[t], sca, s_scb[c + t], s_bias[c + t]);
+                        const float f1 = dequant_value((int)v[t + 1], sca, s_scb[c + t + 1], s_bias[c + t + 1]);
                         w[t >> 1] = pack2<__half>(f0, f1);
-                    else
+                    } else {
+                        // bf16 output, bit-identical to the reference chain (backends/cuda/ops.py:186-210):
+                        // the kernel result is fp16, a non-fp16 bias is added by `out.add_(bias)` on the
+                        // fp16 tensor (fp32 add, one rounding to fp16), then `.to(bfloat16)`.
+                        float f0 = __half2float(__float2half_rn(dequant_value((int)v[t], sca, s_scb[c + t], 0.f)));
+                        float f1 =
+                            __half2float(__float2half_rn(dequant_value((int)v[t + 1], sca, s_scb[c + t + 1], 0.f)));
+                        if (p.bias != nullptr) {
+                            f0 = __half2float(__float2half_rn(f0 + s_bias[c + t]));
+                            f1 = __half2float(__float2half_rn(f1 + s_bias[c + t + 1]));
+                        }
                         w[t >> 1] = pack2<__nv_bfloat16>(f0, f1);
+                    }
                 }
                 uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldc + n;
                 if (n + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {

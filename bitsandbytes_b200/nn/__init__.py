@@ -1,0 +1,9 @@
+from .modules import (  # noqa: F401
+    Int8Params,
+    Linear4bit,
+    Linear8bitLt,
+    LinearFP4,
+    LinearNF4,
+    Params4bit,
+    fix_4bit_weight_quant_state_from_module,
+)

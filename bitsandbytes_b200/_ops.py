@@ -134,7 +134,7 @@ def _(A, threshold=0.0):
 
 def _check_4bit_common(blocksize, quant_type):
     torch._check(quant_type in ("fp4", "nf4"), lambda: f"quant_type must be nf4 or fp4, got {quant_type}")
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
 
 
 @fake("dequantize_4bit")
@@ -169,14 +169,14 @@ def _(A, B, shapeB, absmax, blocksize, quant_type, bias=None, absmax_8bit=None, 
 
 @fake("dequantize_blockwise")
 def _(A, absmax, code, blocksize, dtype):
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
     torch._check(A.dtype == torch.uint8, lambda: f"A must be uint8, got {A.dtype}")
     return torch.empty_like(A, dtype=dtype)
 
 
 @fake("dequantize_blockwise.out")
 def _(A, absmax, code, blocksize, dtype, out):
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
     torch._check(A.dtype == torch.uint8, lambda: f"A must be uint8, got {A.dtype}")
     torch._check(out.shape == A.shape, lambda: f"expected out.shape == {A.shape}, got {out.shape}")
     torch._check(out.dtype == dtype, lambda: f"expected out.dtype == {dtype}, got {out.dtype}")
@@ -184,7 +184,7 @@ def _(A, absmax, code, blocksize, dtype, out):
 
 @fake("quantize_blockwise")
 def _(A, code, blocksize):
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
     n = A.numel()
     return (torch.empty_like(A, dtype=torch.uint8),
             torch.empty((-(n // -blocksize),), device=A.device, dtype=torch.float32))
@@ -198,14 +198,14 @@ def _check_gemv(A, B, shapeB):
 
 @fake("gemv_4bit")
 def _(A, B, shapeB, absmax, code, blocksize):
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
     _check_gemv(A, B, shapeB)
     return torch.empty((*A.shape[:-1], shapeB[0]), device=A.device, dtype=A.dtype)
 
 
 @fake("gemv_4bit.out")
 def _(A, B, shapeB, absmax, code, blocksize, out):
-    torch._check_is_size(blocksize)
+    torch._check(blocksize >= 0, lambda: "blocksize must be non-negative")
     _check_gemv(A, B, shapeB)
     torch._check(out.shape == (*A.shape[:-1], shapeB[0]), lambda: "out has the wrong shape")
     torch._check(out.dtype == A.dtype, lambda: "out must have A's dtype")

@@ -39,7 +39,7 @@ namespace bnb200 {
 
 namespace {
 
-constexpr int kStages = 4;       // pipeline depth (X tiles in smem, W tiles in TMEM)
+constexpr int kStages = 6;       // pipeline depth (X tiles in smem, W tiles in TMEM): covers the TMA latency
 constexpr int kBK = 64;          // k-block: 64 elements = 128 B of 16-bit X per row
 constexpr int kTileN = 128;      // output features per CTA (TMEM lanes)
 constexpr int kDecodeWarps = 8;
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
-    constexpr uint32_t kTmemCols = (MT <= 128) ? 256u : 512u;
-    constexpr uint32_t kWCol0 = (MT <= 128) ? 128u : 256u;  // W stages: kWCol0 + s*32, 32 columns each
+    constexpr uint32_t kTmemCols = 512u;  // D: columns [0, MT); W stages: kWCol0 + s*32, 32 columns each
+    constexpr uint32_t kWCol0 = 256u;
+    static_assert(kWCol0 + kStages * 32 <= kTmemCols, "TMEM budget");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int t = t0 + j;
                 if (t < cnt) {
                     const int i = 2 * t + par;
-                    const int s = i & (kStages - 1);
+                    const int s = i % kStages;
                     const uint32_t ph = (uint32_t)(i / kStages) & 1u;
                     const uint4 q0 = wq[j][0], q1 = wq[j][1];
                     const float sc0 = wsc[j][0], sc1 = wsc[j][1];

@@ -13,38 +13,41 @@
 // B200-first design ("swap-AB, weights through TMEM"):
 //   * The tensor-core M dimension (128 TMEM lanes) carries the OUTPUT FEATURES n; the
 //     tokens m are the UMMA N dimension (16..256).  A CTA owns out[m0:m0+MT, n0:n0+128].
-//   * The packed 4-bit weights never touch shared memory.  Eight decode warps read them
-//     from global (16 B = 32 codes per thread per k-block, prefetched two k-blocks ahead),
-//     expand them warp-locally to T with the exact reference rounding, and write the tile
-//     straight into TENSOR MEMORY with tcgen05.st; tcgen05.mma consumes it as the A operand
-//     ([tmem] form).  Shared memory therefore only carries the activation tile, which is
-//     what limits a Blackwell SM in SS mode.
-//   * The activation tile X[m0:m0+MT, k0:k0+64] arrives by TMA (128-byte swizzle) and is
-//     the B operand (K-major smem descriptor).
-//   * One elected thread issues tcgen05.mma (128 x MT x 16, four per 64-wide k-block) and
-//     frees each pipeline stage with tcgen05.commit -> mbarrier.
+//   * A pipeline stage is 128 k-elements.  The TMA producer stages, per stage, the packed
+//     codes of the CTA's 128 rows (128 x 64 B, 64-byte swizzle, 8 KB) and the activation tile
+//     X[m0:m0+MT, k0:k0+128] (two 128-byte-swizzled sub-tiles).  In a cluster of CL n-tiles
+//     each CTA fetches 1/CL of the activation rows and MULTICASTS them to its peers.
+//   * 16 decode warps (two groups that alternate stages) expand the codes in REGISTERS with
+//     the exact reference rounding -- a per-block 16-entry table built with 16 FMUL + 8
+//     cvt.rn.bf16x2 and looked up with PRMT only -- and write the 16-bit tile straight into
+//     TENSOR MEMORY with tcgen05.st.  tcgen05.mma consumes it as the A operand ([tmem] form):
+//     the decoded weights never pass through shared memory, whose bandwidth is what limits an
+//     SS-mode Blackwell GEMM.  The activation tile is the K-major B operand (smem descriptor).
+//   * One elected thread issues eight tcgen05.mma (128 x MT x 16) per stage behind ONE
+//     mbarrier wait and releases the stage with ONE tcgen05.commit (multicast to the
+//     cluster): synchronisation on the issuing thread was the first bottleneck found.
 //   * Accumulators (128 lanes x MT fp32 columns) live in TMEM; the decode warps become the
 //     epilogue warps: tcgen05.ld -> +bias -> rn_T -> global, or -- for split-K, which fills
 //     the 148 SMs when M is small -- fp32 partials to an L2-resident workspace with a
 //     last-arriver reduction in deterministic split order.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
-// warps 2..9 decode / epilogue (TMEM lane quarter = warp_id % 4, k-half = (warp_id-2)/4).
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
+// warps 2..17 decode / epilogue (TMEM lane quarter = warp_id % 4).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace bnb200 {
 
 namespace {
 
-constexpr int kStages = 6;       // pipeline depth (X tiles in smem, W tiles in TMEM): covers the TMA latency
-constexpr int kBK = 64;          // k-block: 64 elements = 128 B of 16-bit X per row
+constexpr int kBK = 128;         // pipeline stage: 128 k-elements = two 128-byte swizzle atoms of X per row
 constexpr int kTileN = 128;      // output features per CTA (TMEM lanes)
-constexpr int kDecodeWarps = 8;
+constexpr int kDecodeWarps = 16;  // two groups of 8: group g decodes the stages i with i % 2 == g
 constexpr int kThreads = 32 * (2 + kDecodeWarps);
-constexpr int kPrefetch = 4;     // decode-side global prefetch distance (k-blocks of one warp set)
+constexpr int kScaleDepth = 4;   // decode-side register ring for the per-block scales (stages of one group)
 
 struct Gemm4Params {
     const uint8_t* B;            // packed codes [N, K/2]
@@ -58,9 +61,10 @@ struct Gemm4Params {
     int* ws_counter;             // one per output tile, zero on entry, reset on exit
     int M, N, K, ldc;
     int log2_bs;
-    int kblocks_total;           // K / 64
+    int kblocks_total;           // number of 128-wide stages = ceil(K / 128)
     int kblocks_per_split;
     int splits;
+    int debug;                   // developer knobs (BNB_B200_DEBUG): 1 skip decode math, 2 skip tcgen05.st, 4 skip TMA, 8 skip MMA
 };
 
 template <typename T> struct TcFmt;
@@ -131,26 +135,45 @@ __device__ __forceinline__ void decode_word(uint32_t w, const DecodeTable& t, ui
     }
 }
 
-template <typename T, int QT, int MT>
+// Pipeline stage = 128 k-elements: two 64-wide (128-byte, swizzle-atom) activation sub-tiles in
+// shared memory and 64 TMEM columns of decoded weights.  One `full` and one `empty` mbarrier per
+// stage keep the synchronisation cost on the single MMA-issuing thread at one wait + one commit
+// per eight tcgen05.mma (it was the bottleneck with 64-wide stages and separate barriers).
+template <int MT> struct StageCfg {
+    static constexpr int kStages = (MT == 256) ? 3 : 4;          // smem: kStages * (MT * 256 + 8192) B <= 216 KB
+    static constexpr int kXSubBytes = MT * 128;                  // one 64-wide sub-tile
+    static constexpr int kXStageBytes = 2 * kXSubBytes;
+    static constexpr int kWStageBytes = kTileN * 64;             // packed codes: 128 rows x 64 B (TMA, 64-B swizzle)
+    static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
+    static constexpr uint32_t kTmemCols = 512u;                  // D: [0, MT); W stage s: kWCol0 + 64 s
+    static constexpr uint32_t kWCol0 = 256u;
+    static_assert(kWCol0 + kStages * 64 <= kTmemCols, "TMEM budget");
+};
+
+template <typename T, int QT, int MT, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Gemm4Params p) {
+    gemm4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const Gemm4Params p) {
+    using Cfg = StageCfg<MT>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kXSubBytes = Cfg::kXSubBytes;
+    constexpr int kXStageBytes = Cfg::kXStageBytes;
+    constexpr uint32_t kTmemCols = Cfg::kTmemCols;
+    constexpr uint32_t kWCol0 = Cfg::kWCol0;
+
     // ------------------------------------------------------------------ shared memory
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // X stages: MT rows x 128 B each, 1024-B aligned (MT >= 16 -> multiple of 2048 B)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kXStageBytes = MT * 128;
-    uint8_t* sx = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kXStageBytes);
-    uint64_t* full_x = bars;                  // [kStages] TMA -> MMA
-    uint64_t* full_w = bars + kStages;        // [kStages] decode -> MMA   (count = kDecodeWarps / 2)
-    uint64_t* empty = bars + 2 * kStages;     // [kStages] MMA -> TMA + decode (tcgen05.commit)
-    uint64_t* acc_full = bars + 3 * kStages;  // MMA -> epilogue
+    constexpr int kWStageBytes = Cfg::kWStageBytes;
+    uint8_t* sx = smem;                              // [kStages][2][MT x 128 B]   activations
+    uint8_t* sw = smem + kStages * kXStageBytes;     // [kStages][128 x 64 B]      packed codes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full = bars;                   // [kStages] TMA (1 arrive + X bytes) + the 8 warps of one decode group -> MMA
+    uint64_t* empty = bars + kStages;        // [kStages] MMA of every cluster CTA -> TMA producer + decode warps
+    uint64_t* w_full = bars + 2 * kStages;   // [kStages] TMA (1 arrive + W bytes) -> decode warps
+    uint64_t* acc_full = bars + 3 * kStages; // MMA -> epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-
-    constexpr uint32_t kTmemCols = 512u;  // D: columns [0, MT); W stages: kWCol0 + s*32, 32 columns each
-    constexpr uint32_t kWCol0 = 256u;
-    static_assert(kWCol0 + kStages * 32 <= kTmemCols, "TMEM budget");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -158,18 +181,21 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int n0 = blockIdx.x * kTileN;
     const int m0 = blockIdx.y * MT;
     const int split = blockIdx.z;
-    const int kb_begin = split * p.kblocks_per_split;
-    int kb_end = kb_begin + p.kblocks_per_split;
-    if (kb_end > p.kblocks_total) kb_end = p.kblocks_total;
-    const int nkb = kb_end - kb_begin;  // >= 1 by construction
+    // work is split in 128-wide stages; kb64_* count 64-wide k-blocks
+    const int st_begin = split * p.kblocks_per_split;
+    int st_end = st_begin + p.kblocks_per_split;
+    if (st_end > p.kblocks_total) st_end = p.kblocks_total;
+    const int nst = st_end - st_begin;  // >= 1 by construction
+    const int kb64_total = p.K / 64;    // the last stage may hold a single 64-wide block
 
     // ------------------------------------------------------------------ setup
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(&full_x[s], 1);
-            ptx::mbar_init(&full_w[s], kDecodeWarps / 2);
-            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init(&full[s], 1 + kDecodeWarps / 2);
+            ptx::mbar_init(&empty[s], CL);
+            ptx::mbar_init(&w_full[s], 1);
         }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
@@ -179,19 +205,51 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) {
+        ptx::cluster_sync();  // peers' barriers are initialised before anyone multicasts / arrives remotely
+    } else {
+        __syncthreads();
+    }
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+    const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ================================================================== TMA producer
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                ptx::mbar_wait(&empty[s], ph ^ 1u);
-                ptx::mbar_arrive_expect_tx(&full_x[s], kXStageBytes);
-                ptx::tma_load_2d(sx + s * kXStageBytes, &tmap_x, &full_x[s], (kb_begin + i) * kBK, m0);
+            for (int i = 0; i < nst; ++i) {
+                ptx::mbar_wait(&empty[s], ph ^ 1u);  // every CTA of the cluster has consumed this stage
+                const int k0 = (st_begin + i) * kBK;
+                if (p.debug & 32) {
+                    ptx::mbar_arrive(&w_full[s]);
+                } else {
+                    // packed codes of this CTA's 128 output features: bytes [k0/2, k0/2 + 64) of rows n0..n0+127
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kWStageBytes);
+                    ptx::tma_load_2d(sw + s * kWStageBytes, &tmap_w, &w_full[s], k0 / 2, n0);
+                }
+                if (p.debug & 4) {
+                    ptx::mbar_arrive(&full[s]);
+                } else {
+                    ptx::mbar_arrive_expect_tx(&full[s], kXStageBytes);
+                    uint8_t* dst = sx + s * kXStageBytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // columns past K are out of bounds for the tensor map: TMA zero-fills them
+                        if constexpr (CL == 1) {
+                            ptx::tma_load_2d(dst + h * kXSubBytes, &tmap_x, &full[s], k0 + 64 * h, m0);
+                        } else {
+                            // this CTA fetches rows [rank*MT/CL, +MT/CL) once from L2 and multicasts them
+                            // into the same stage of every CTA of the cluster
+                            constexpr int kSliceRows = MT / CL;
+                            ptx::tma_load_2d_multicast(dst + h * kXSubBytes + cta_rank * (kSliceRows * 128), &tmap_x,
+                                                       &full[s], k0 + 64 * h, m0 + (int)cta_rank * kSliceRows,
+                                                       kClusterMask);
+                        }
+                    }
+                }
                 if (++s == kStages) {
                     s = 0;
                     ph ^= 1u;
@@ -203,20 +261,28 @@ __global__ void __launch_bounds__(kThreads, 1)
         constexpr uint32_t idesc = ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/128, /*N=*/MT);
         int s = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < nkb; ++i) {
-            ptx::mbar_wait(&full_x[s], ph);
-            ptx::mbar_wait(&full_w[s], ph);
+        for (int i = 0; i < nst; ++i) {
+            ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
             if (lane == 0) {
-                const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sx + s * kXStageBytes));
-                const uint32_t a_tmem = tmem_base + kWCol0 + s * 32;
+                const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
+                const uint64_t bdesc0 = ptx::make_sw128_kmajor_desc(xs);
+                const uint64_t bdesc1 = ptx::make_sw128_kmajor_desc(xs + kXSubBytes);
+                const uint32_t a_tmem = tmem_base + kWCol0 + s * 64;
+                if (!(p.debug & 8)) {
 #pragma unroll
-                for (int j = 0; j < kBK / 16; ++j) {
-                    // K advances by 16 elements: +8 TMEM columns for A, +32 B (2 x 16 B) for B
-                    ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
+                    for (int j = 0; j < 8; ++j) {
+                        // K advances by 16 elements: +8 TMEM columns for A, +32 B (2 x 16 B) inside a sub-tile
+                        ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3), idesc,
+                                        (i | j) != 0 ? 1u : 0u);
+                    }
                 }
-                ptx::tc_commit(&empty[s]);
-                if (i == nkb - 1) ptx::tc_commit(acc_full);
+                if constexpr (CL == 1) {
+                    ptx::tc_commit(&empty[s]);
+                } else {
+                    ptx::tc_commit_multicast(&empty[s], kClusterMask);
+                }
+                if (i == nst - 1) ptx::tc_commit(acc_full);
             }
             __syncwarp();
             if (++s == kStages) {
@@ -226,83 +292,90 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else {
         // ================================================================== decode warps
-        const int dw = warp - 2;          // 0..7
+        const int dw = warp - 2;          // 0..15
         const int quarter = warp & 3;     // TMEM lane quarter this warp may touch
-        const int par = dw >> 2;          // warp set: handles k-blocks i with (i & 1) == par
-        const int khalf = par;            // epilogue: which half of the accumulator columns
+        const int grp = dw >> 3;          // decode group: owns the stages with (stage & 1) == grp
+        const int half = (dw >> 2) & 1;   // which 64 of the stage's 128 k-elements
+        const int khalf = dw >> 2;        // epilogue: which quarter of the accumulator columns (0..3)
         const int row = quarter * 32 + lane;
         const int n = n0 + row;
         const bool n_ok = n < p.N;
-        const uint8_t* wrow = p.B + ((long long)(n_ok ? n : 0) * p.K >> 1);
         const long long e_row = (long long)(n_ok ? n : 0) * p.K;
         ScaleSrc sc{p.absmax, p.absmax_8bit, p.absmax_code, p.absmax_offset ? __ldg(p.absmax_offset) : 0.0f};
-        const bool two_scales = p.log2_bs == 5;  // blocksize 32: two quantisation blocks per 64-wide k-block
+        const bool two_scales = p.log2_bs == 5;  // blocksize 32: two quantisation blocks per 64 codes
 
-        // This warp set's k-blocks: i = 2 t + par, t = 0 .. cnt-1.
-        const int cnt = (nkb - par + 1) >> 1;
+        // The packed codes arrive by TMA (64-byte swizzle: 16-byte chunk c of row r sits at chunk
+        // c ^ ((r >> 1) & 3)); this thread owns chunks 2*half and 2*half+1 of its row.
+        const uint32_t sw_row = (uint32_t)row * 64u;
+        const uint32_t sw_c0 = (uint32_t)(((2 * half) ^ ((row >> 1) & 3)) * 16);
+        const uint32_t sw_c1 = (uint32_t)(((2 * half + 1) ^ ((row >> 1) & 3)) * 16);
 
-        // Register prefetch ring, kPrefetch of this warp set's k-blocks deep.  The loop is unrolled
-        // by kPrefetch so that slot j is a fixed set of registers: no register rotation (a move out
-        // of a load's destination would wait for the load and collapse the prefetch).
-        uint4 wq[kPrefetch][2];
-        float wsc[kPrefetch][2];
-#pragma unroll
-        for (int j = 0; j < kPrefetch; ++j) {
-            wq[j][0] = wq[j][1] = make_uint4(0, 0, 0, 0);
+        // Scales are scattered 4-byte loads (one row per lane): a register ring kScaleDepth stages
+        // deep hides their latency.  The loop is unrolled by the ring depth so that slot j is a fixed
+        // register (no rotation: a move out of a load's destination would wait for the load).
+        float wsc[kScaleDepth][2];
+        auto fetch = [&](int j, int t) {
             wsc[j][0] = wsc[j][1] = 0.f;
-            if (j < cnt && n_ok) {
-                const int kb = kb_begin + 2 * j + par;
-                const uint8_t* src = wrow + (long long)kb * (kBK / 2);
-                wq[j][0] = ldg_stream_v4(src);
-                wq[j][1] = ldg_stream_v4(src + 16);
-                const long long e = e_row + (long long)kb * kBK;
+            const int stage_idx = 2 * t + grp;                 // this group's t-th stage
+            const int kb = 2 * (st_begin + stage_idx) + half;  // 64-wide k-block of this warp
+            if (stage_idx < nst && n_ok && kb < kb64_total) {
+                const long long e = e_row + (long long)kb * 64;
                 wsc[j][0] = sc.load(e >> p.log2_bs);
                 if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
             }
-        }
-
-        for (int t0 = 0; t0 < cnt; t0 += kPrefetch) {
+        };
 #pragma unroll
-            for (int j = 0; j < kPrefetch; ++j) {
+        for (int j = 0; j < kScaleDepth; ++j) fetch(j, j);
+
+        const int cnt = (nst - grp + 1) >> 1;  // number of stages this group owns
+        for (int t0 = 0; t0 < cnt; t0 += kScaleDepth) {
+#pragma unroll
+            for (int j = 0; j < kScaleDepth; ++j) {
                 const int t = t0 + j;
                 if (t < cnt) {
-                    const int i = 2 * t + par;
+                    const int i = 2 * t + grp;
                     const int s = i % kStages;
                     const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-                    const uint4 q0 = wq[j][0], q1 = wq[j][1];
                     const float sc0 = wsc[j][0], sc1 = wsc[j][1];
-                    if (t + kPrefetch < cnt && n_ok) {
-                        const int kb = kb_begin + 2 * (t + kPrefetch) + par;
-                        const uint8_t* src = wrow + (long long)kb * (kBK / 2);
-                        wq[j][0] = ldg_stream_v4(src);
-                        wq[j][1] = ldg_stream_v4(src + 16);
-                        const long long e = e_row + (long long)kb * kBK;
-                        wsc[j][0] = sc.load(e >> p.log2_bs);
-                        if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
+                    fetch(j, t + kScaleDepth);
+
+                    ptx::mbar_wait(&w_full[s], ph);  // this stage's codes have landed
+                    const uint8_t* wt = sw + s * kWStageBytes + sw_row;
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(wt + sw_c0);
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(wt + sw_c1);
+
+                    // 64 codes of row n -> 32 registers of T pairs.  (Rows past N and k-blocks past K are
+                    // zero-filled by TMA and carry scale 0: they decode to +-0.)
+                    uint32_t r[32];
+                    if (p.debug & 1) {
+#pragma unroll
+                        for (int z = 0; z < 32; ++z) r[z] = q0.x + z;
+                    } else {
+                        DecodeTable tab;
+                        build_table<T, QT>(sc0, tab);
+                        decode_word(q0.x, tab, r + 0);
+                        decode_word(q0.y, tab, r + 4);
+                        decode_word(q0.z, tab, r + 8);
+                        decode_word(q0.w, tab, r + 12);
+                        if (two_scales) build_table<T, QT>(sc1, tab);
+                        decode_word(q1.x, tab, r + 16);
+                        decode_word(q1.y, tab, r + 20);
+                        decode_word(q1.z, tab, r + 24);
+                        decode_word(q1.w, tab, r + 28);
                     }
 
-                    // 64 codes of row n -> 32 registers of T pairs
-                    uint32_t r[32];
-                    DecodeTable tab;
-                    build_table<T, QT>(sc0, tab);
-                    decode_word(q0.x, tab, r + 0);
-                    decode_word(q0.y, tab, r + 4);
-                    decode_word(q0.z, tab, r + 8);
-                    decode_word(q0.w, tab, r + 12);
-                    if (two_scales) build_table<T, QT>(sc1, tab);
-                    decode_word(q1.x, tab, r + 16);
-                    decode_word(q1.y, tab, r + 20);
-                    decode_word(q1.z, tab, r + 24);
-                    decode_word(q1.w, tab, r + 28);
-
-                    ptx::mbar_wait(&empty[s], ph ^ 1u);  // the MMAs that read this TMEM stage have retired
+                    // w_full[s] completing implies the producer saw empty[s]; waiting on it here as well
+                    // makes this warp itself an observer of the MMA completion before it overwrites TMEM.
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::tc_fence_after();
-                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 32;
-                    ptx::tmem_st_x32(taddr, r);
-                    ptx::tmem_wait_st();
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 64 + half * 32;
+                    if (!(p.debug & 2)) {
+                        ptx::tmem_st_x32(taddr, r);
+                        ptx::tmem_wait_st();
+                    }
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&full_w[s]);
+                    if (lane == 0) ptx::mbar_arrive(&full[s]);
                 }
             }
         }
@@ -312,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_after();
 
         // this warp: lanes [quarter*32, +32) (= output features), columns [khalf*MT/2, +MT/2)
-        constexpr int kColsPerWarp = MT / 2;
+        constexpr int kColsPerWarp = MT / 4;
         constexpr int kChunk = (kColsPerWarp >= 32) ? 32 : kColsPerWarp;  // 8 (MT=16), 16, 32
         const int col0 = khalf * kColsPerWarp;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
@@ -336,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int t = 0; t < kChunk; ++t) {
                     const int m = m0 + col0 + c + t;
-                    if (n_ok && m < p.M)
+                    if (n_ok && m < p.M && !(p.debug & 16))
                         outp[(long long)m * p.ldc + n] = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
                 }
             }
@@ -363,13 +436,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             __threadfence();
             // named barrier over the 8 epilogue warps (256 threads); barrier 0 is __syncthreads
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (threadIdx.x == 64) {
                 int prev = atomicAdd(p.ws_counter + tile_id, 1);
                 *s_flag = (prev == p.splits - 1) ? 1 : 0;
                 if (prev == p.splits - 1) p.ws_counter[tile_id] = 0;  // self-reset for the next launch
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (*s_flag) {
                 __threadfence();
                 const float* base = p.ws_partial + ((long long)(tile_id * p.splits) * kTileN + row) * MT;
@@ -397,7 +470,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     // ------------------------------------------------------------------ teardown
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) {
+        ptx::cluster_sync();  // no CTA may exit while peers can still multicast into / arrive on its smem
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
@@ -476,11 +553,20 @@ Workspace* get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_cou
     return &e->ws;
 }
 
-template <typename T, int QT, int MT>
-bool launch_mt(const CUtensorMap& tmap, Gemm4Params& p, cudaStream_t stream) {
-    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(kStages) * MT * 128 + 256 /*barriers*/;
+int cluster_override() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("BNB_B200_CLUSTER");
+        v = e ? atoi(e) : -1;
+    }
+    return v;
+}
+
+template <typename T, int QT, int MT, int CL>
+bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
+    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(StageCfg<MT>::kStages) * StageCfg<MT>::kStageBytes + 256 /*barriers*/;
     static bool attr_set = false;
-    auto kern = gemm4_tc_kernel<T, QT, MT>;
+    auto kern = gemm4_tc_kernel<T, QT, MT, CL>;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("gemm4_tc smem attr", cudaGetLastError());
@@ -488,18 +574,24 @@ bool launch_mt(const CUtensorMap& tmap, Gemm4Params& p, cudaStream_t stream) {
         }
         attr_set = true;
     }
+    CUtensorMap tmap, tmap_w;
+    if (!encode_tmap_2d(&tmap, A, 2, 128, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)(MT / CL), 64u)) {
+        return false;
+    }
+    // packed codes as a [N, K/2] byte matrix, 128 x 64-byte boxes, 64-byte swizzle
+    if (!encode_tmap_2d(&tmap_w, p.B, 1, 64, (uint64_t)p.N, (uint64_t)p.K / 2, (uint64_t)p.K / 2, (uint32_t)kTileN, 64u)) {
+        return false;
+    }
     const int n_tiles = (p.N + kTileN - 1) / kTileN;
     const int m_tiles = (p.M + MT - 1) / MT;
 
-    // split-K so that small problems still cover the machine: target >= ~1 CTA per SM,
-    // at least 4 k-blocks per split.
+    // split-K so that small problems still cover the machine in one wave, >= 4 k-blocks per split
     const int sms = device_sm_count();
     int splits = 1;
     const int tiles = n_tiles * m_tiles;
     if (tiles * 2 <= sms) {
-        // one wave: the largest split count whose grid still fits the machine
         splits = sms / tiles;
-        int max_by_k = p.kblocks_total / 4;
+        int max_by_k = p.kblocks_total / 2;  // >= two 128-wide stages per split
         if (max_by_k < 1) max_by_k = 1;
         if (splits > max_by_k) splits = max_by_k;
         if (splits > 16) splits = 16;
@@ -520,8 +612,24 @@ bool launch_mt(const CUtensorMap& tmap, Gemm4Params& p, cudaStream_t stream) {
         p.ws_partial = reinterpret_cast<float*>(ws->ptr);
         p.ws_counter = ws->counters;
     }
-    dim3 grid(n_tiles, m_tiles, splits);
-    kern<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_tiles, m_tiles, splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_w, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_last_error("gemm4_tc launch", e);
+        return false;
+    }
     BNB200_CHECK_LAUNCH("gemm4_tc");
     return true;
 }
@@ -534,7 +642,7 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
                      int ldc, int blocksize, int quant_type, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return true;
-    if (K < kBK || (K % kBK) != 0) return false;
+    if (K < 64 || (K % 64) != 0) return false;
     if (blocksize < 32 || (blocksize & (blocksize - 1)) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(B) & 15) != 0) return false;
     if (quant_type != kNF4 && quant_type != kFP4) return false;
@@ -545,11 +653,6 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     else if (M <= 64) MT = 64;
     else if (M <= 128) MT = 128;
 
-    CUtensorMap tmap;
-    if (!encode_tmap_2d(&tmap, A, 2, false, std::is_same<T, __half>::value, (uint64_t)M, (uint64_t)K,
-                        (uint64_t)K * 2, (uint32_t)MT, (uint32_t)kBK)) {
-        return false;
-    }
     Gemm4Params p{};
     p.B = B;
     p.absmax = absmax;
@@ -563,15 +666,40 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     p.K = K;
     p.ldc = ldc;
     p.log2_bs = ilog2_pow2(blocksize);
-    p.kblocks_total = K / kBK;
+    p.kblocks_total = (K + kBK - 1) / kBK;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("BNB_B200_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug = dbg;
+    }
+
+    // Cluster of CL n-tiles sharing one activation tile by TMA multicast: only worth it when the
+    // activation tile is the dominant L2 traffic (large M) and the n-tile count divides.
+    const int n_tiles = (N + kTileN - 1) / kTileN;
+    int CL = 1;
+    if (MT >= 128) {
+        if (n_tiles % 4 == 0) CL = 4;
+        else if (n_tiles % 2 == 0) CL = 2;
+    }
+    const int ov = cluster_override();
+    if (ov == 1 || (ov == 2 && n_tiles % 2 == 0 && MT >= 128) || (ov == 4 && n_tiles % 4 == 0 && MT >= 128)) CL = ov;
 
 #define BNB200_DISPATCH_MT(QT)                                                                                         \
     switch (MT) {                                                                                                      \
-    case 16: return launch_mt<T, QT, 16>(tmap, p, stream);                                                             \
-    case 32: return launch_mt<T, QT, 32>(tmap, p, stream);                                                             \
-    case 64: return launch_mt<T, QT, 64>(tmap, p, stream);                                                             \
-    case 128: return launch_mt<T, QT, 128>(tmap, p, stream);                                                           \
-    default: return launch_mt<T, QT, 256>(tmap, p, stream);                                                            \
+    case 16: return launch_mt<T, QT, 16, 1>(A, p, stream);                                                             \
+    case 32: return launch_mt<T, QT, 32, 1>(A, p, stream);                                                             \
+    case 64: return launch_mt<T, QT, 64, 1>(A, p, stream);                                                             \
+    case 128:                                                                                                          \
+        if (CL == 4) return launch_mt<T, QT, 128, 4>(A, p, stream);                                                    \
+        if (CL == 2) return launch_mt<T, QT, 128, 2>(A, p, stream);                                                    \
+        return launch_mt<T, QT, 128, 1>(A, p, stream);                                                                 \
+    default:                                                                                                           \
+        if (CL == 4) return launch_mt<T, QT, 256, 4>(A, p, stream);                                                    \
+        if (CL == 2) return launch_mt<T, QT, 256, 2>(A, p, stream);                                                    \
+        return launch_mt<T, QT, 256, 1>(A, p, stream);                                                                 \
     }
     if (quant_type == kNF4) {
         BNB200_DISPATCH_MT(kNF4)

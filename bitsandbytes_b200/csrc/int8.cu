@@ -441,8 +441,8 @@ int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const
     if (K <= 0 || (K % 16) != 0) return 100;
     if ((reinterpret_cast<uintptr_t>(acts) & 15) != 0 || (reinterpret_cast<uintptr_t>(weights) & 15) != 0) return 100;
     CUtensorMap ta, tb;
-    if (!encode_tmap_2d(&ta, acts, 1, true, false, (uint64_t)M, (uint64_t)K, (uint64_t)K, kI8TileM, kI8BK)) return 100;
-    if (!encode_tmap_2d(&tb, weights, 1, true, false, (uint64_t)N, (uint64_t)K, (uint64_t)K, kI8TileN, kI8BK))
+    if (!encode_tmap_2d(&ta, acts, 1, 128, (uint64_t)M, (uint64_t)K, (uint64_t)K, kI8TileM, kI8BK)) return 100;
+    if (!encode_tmap_2d(&tb, weights, 1, 128, (uint64_t)N, (uint64_t)K, (uint64_t)K, kI8TileN, kI8BK))
         return 100;
     I8Params p{};
     p.out = out;

@@ -75,6 +75,29 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                  : "memory");
 }
 
+
+// Multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`
+// and performs complete_tx on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner,
+                                                      int c_outer, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCols> __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -108,6 +131,16 @@ __device__ __forceinline__ void tc_fence_after() {
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+
+// Same, arriving on the mbarrier at the same offset in every CTA of `cta_mask` (cluster-wide
+// release of a multicast-filled shared-memory stage).
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(smem_u32(bar)),
+                 "h"(cta_mask)
                  : "memory");
 }
 
@@ -224,8 +257,8 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t d_fmt, uint32_t a_fmt
 
 // ---------------------------------------------------------------- host: tensor maps
 // Encodes a 2-D row-major [rows, cols] tensor of `elem_bytes`-byte elements with a
-// [box_rows, box_cols] box and the 128-byte swizzle.  Returns false on failure.
-bool encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, bool is_int8, bool is_fp16, uint64_t rows,
-                    uint64_t cols, uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
+// [box_rows, box_cols] box and the 128- or 64-byte swizzle.  Returns false on failure.
+bool encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
 
 } // namespace bnb200

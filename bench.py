@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=32, help="llama8b workload: number of decoder layers")
     return ap.parse_args()
 
 
@@ -175,9 +176,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "sharded70b":
-        from bitsandbytes_b200.bench_sharded import run_sharded70b  # noqa: WPS433
+        from bitsandbytes_b200.bench_sharded import run_sharded70b
 
         return run_sharded70b(args, rank, world, local_rank)
+    if args.workload == "llama8b":
+        from bitsandbytes_b200.bench_e2e import run_llama8b
+
+        return run_llama8b(args, rank, world, local_rank)
     N, K, M, qt, nested = WORKLOADS[args.workload]
 
     import torch

@@ -34,6 +34,7 @@
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
 // warps 2..17 decode / epilogue (TMEM lane quarter = warp_id % 4).
 #include "common.cuh"
+#include "decode4.cuh"
 #include "sm100_ptx.cuh"
 
 #include <cstdlib>
@@ -71,69 +72,7 @@ template <typename T> struct TcFmt;
 template <> struct TcFmt<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
 template <> struct TcFmt<__half> { static constexpr uint32_t kFmt = 0; };
 
-struct ScaleSrc {
-    const float* absmax;
-    const uint8_t* absmax_8bit;
-    const float* absmax_code;
-    float offset;
-    __device__ __forceinline__ float load(long long idx) const {
-        if (absmax_8bit != nullptr) {
-            const float c = __ldg(absmax_code + __ldg(absmax_8bit + idx));
-            return __fadd_rn(mul_ftz(c, __ldg(absmax + (idx >> 8))), offset);
-        }
-        return __ldg(absmax + idx);
-    }
-};
 
-// NOTE on the nested (double-quant) scale: the reference has two behaviours.  Its fused
-// kernels write `code[q] * absmax2 + offset`, which nvcc contracts to one fma
-// (gemm_4bit_sm80.cu:292-297); its dequantize + F.linear path -- the one B200 takes for
-// M > 4 (backends/cuda/ops.py:617-623, 904-916) and the one F.dequantize_4bit exposes --
-// rounds the product and the sum separately.  We follow the second (mul, then add), so the
-// fused GEMM sees exactly the weights F.dequantize_4bit returns.
-
-
-// ---------------------------------------------------------------- register-resident decode
-// W_T = rn_T(value(code) * scale) takes only 16 distinct values per quantisation block, so a
-// decode thread first builds that 16-entry table (16 fp32 multiplies by immediates, 8 packed
-// roundings -- bit-identical to rounding every element) and keeps it in 8 registers as two
-// byte planes (low bytes / high bytes of the 16-bit entries).  Codes are then translated with
-// PRMT (byte permute) only: no shared-memory look-up table, hence no bank conflicts and no
-// competition with the tensor core for shared-memory bandwidth.
-struct DecodeTable {
-    uint32_t lo[4];  // lo[j] = low bytes of entries 4j .. 4j+3
-    uint32_t hi[4];  // hi[j] = high bytes
-};
-
-template <typename T, int QT> __device__ __forceinline__ void build_table(float scale, DecodeTable& t) {
-    uint32_t pr[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        pr[j] = pack2<T>(mul_ftz(code4_value<QT>(2 * j), scale), mul_ftz(code4_value<QT>(2 * j + 1), scale));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        t.lo[j] = __byte_perm(pr[2 * j], pr[2 * j + 1], 0x6420);
-        t.hi[j] = __byte_perm(pr[2 * j], pr[2 * j + 1], 0x7531);
-    }
-}
-
-// One packed word = 4 bytes = 8 codes (byte b: element 2b in the high nibble) -> 4 registers of
-// T pairs, element 2b in the low half.  Selector nibbles must stay < 8 (bit 3 is PRMT's
-// sign-replicate flag): `c` carries code & 7, `selm` picks between the idx<8 / idx>=8 halves.
-__device__ __forceinline__ void decode_word(uint32_t w, const DecodeTable& t, uint32_t* o) {
-    const uint32_t c7 = w & 0x77777777u;
-    const uint32_t w1 = w >> 1;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const uint32_t c = g ? (c7 >> 16) : c7;
-        const uint32_t m = g ? (w1 >> 16) : w1;
-        const uint32_t selm = (m & 0x4444u) | 0x3210u;
-        const uint32_t lo = __byte_perm(__byte_perm(t.lo[0], t.lo[1], c), __byte_perm(t.lo[2], t.lo[3], c), selm);
-        const uint32_t hi = __byte_perm(__byte_perm(t.hi[0], t.hi[1], c), __byte_perm(t.hi[2], t.hi[3], c), selm);
-        o[2 * g] = __byte_perm(lo, hi, 0x4051);      // (T[hi nibble of byte 0], T[lo nibble of byte 0])
-        o[2 * g + 1] = __byte_perm(lo, hi, 0x6273);  // byte 1
-    }
-}
 
 // Pipeline stage = 128 k-elements: two 64-wide (128-byte, swizzle-atom) activation sub-tiles in
 // shared memory and 64 TMEM columns of decoded weights.  One `full` and one `empty` mbarrier per

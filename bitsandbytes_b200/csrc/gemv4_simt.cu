@@ -15,6 +15,9 @@
 // gemm_4bit_simt.cu:353,452-453):  W_T = rn_T(value * scale), fp32 fma accumulation, bias
 // added in fp32, one rounding to T.  For T = fp32 there is no weight rounding.
 #include "common.cuh"
+#include "decode4.cuh"
+
+#include <type_traits>
 
 namespace bnb200 {
 
@@ -175,6 +178,108 @@ __device__ __forceinline__ void
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Decode-time GEMV (M <= 8, 16-bit activations): HBM-bound streaming of the packed weight.
+//
+// One warp per output feature.  Each lane owns 32 consecutive k (one 16-byte load of codes,
+// one scale when blocksize >= 32); a warp covers 1024 k per step and issues the loads of
+// kSteps steps before touching any of them, so ~2 KB per warp (>= 50 KB per SM) is in flight.
+// Codes are expanded with the same register-resident PRMT table as the tensor-core kernel
+// (bit-identical weights), widened to fp32 and accumulated with FFMA; activations come
+// through L1 (they are M x K x 2 bytes, re-read by every warp).
+// ---------------------------------------------------------------------------------------
+constexpr int kFastSteps = 4;
+
+template <typename T> __device__ __forceinline__ void widen2(uint32_t pair, float& lo, float& hi);
+template <> __device__ __forceinline__ void widen2<__nv_bfloat16>(uint32_t pair, float& lo, float& hi) {
+    lo = __uint_as_float(pair << 16);
+    hi = __uint_as_float(pair & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void widen2<__half>(uint32_t pair, float& lo, float& hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pair));
+    lo = f.x;
+    hi = f.y;
+}
+
+template <typename T, int QT, int MB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+    gemv4_fast_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, const float* absmax,
+                      const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset,
+                      T* __restrict__ out, const T* __restrict__ bias, int M, int N, int K, int ldc, int log2_bs) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (n >= N) return;
+    ScaleSrc sc{absmax, absmax_8bit, absmax_code,
+                (absmax_8bit != nullptr && absmax_offset != nullptr) ? __ldg(absmax_offset) : 0.f};
+    // 32 codes per lane never straddle a quantisation block (blocksize >= 32, K % 32 == 0)
+    const long long e_row = (long long)n * K;
+    const uint8_t* brow = B + (e_row >> 1);
+
+    float acc[MB];
+#pragma unroll
+    for (int i = 0; i < MB; ++i) acc[i] = 0.f;
+
+    for (int k_base = 0; k_base < K; k_base += 1024 * kFastSteps) {
+        uint4 q[kFastSteps];
+        float s[kFastSteps];
+#pragma unroll
+        for (int u = 0; u < kFastSteps; ++u) {
+            const int k0 = k_base + u * 1024 + lane * 32;
+            q[u] = make_uint4(0, 0, 0, 0);
+            s[u] = 0.f;
+            if (k0 < K) {
+                q[u] = ldg_stream_v4(brow + (k0 >> 1));
+                s[u] = sc.load((e_row + k0) >> log2_bs);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFastSteps; ++u) {
+            const int k0 = k_base + u * 1024 + lane * 32;
+            if (k0 < K) {
+                uint32_t r[16];
+                DecodeTable tab;
+                build_table<T, QT>(s[u], tab);
+                decode_word(q[u].x, tab, r + 0);
+                decode_word(q[u].y, tab, r + 4);
+                decode_word(q[u].z, tab, r + 8);
+                decode_word(q[u].w, tab, r + 12);
+                float w[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) widen2<T>(r[j], w[2 * j], w[2 * j + 1]);
+#pragma unroll
+                for (int i = 0; i < MB; ++i) {
+                    if (i < M) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(A + (long long)i * K + k0);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const uint4 av = __ldg(ap + v);
+                            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float a0, a1;
+                                widen2<T>(aw[t], a0, a1);
+                                acc[i] = fmaf(a0, w[8 * v + 2 * t], acc[i]);
+                                acc[i] = fmaf(a1, w[8 * v + 2 * t + 1], acc[i]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MB; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane == 0) {
+        const float b = bias != nullptr ? DT<T>::to_f32(bias[n]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+            if (i < M) out[(long long)i * ldc + n] = DT<T>::from_f32(acc[i] + b);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
     gemv4_simt_kernel(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
@@ -193,6 +298,33 @@ void launch_gemv4_simt(const T* A, const uint8_t* B, const float* absmax, const 
                        const float* absmax_code, const float* absmax_offset, const float* lut16, int quant_type,
                        T* out, const T* bias, int M, int N, int K, int ldc, int blocksize, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return;
+    if constexpr (!std::is_same<T, float>::value) {
+        const bool pow2 = blocksize >= 32 && (blocksize & (blocksize - 1)) == 0;
+        const bool fast_ok = lut16 == nullptr && M <= 8 && (K % 32 == 0) && pow2 &&
+                             ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) &&
+                             (quant_type == kNF4 || quant_type == kFP4);
+        if (fast_ok) {
+            const dim3 g((N + kWarpsPerCta - 1) / kWarpsPerCta);
+            const int l2 = ilog2_pow2(blocksize);
+#define BNB200_FAST(QT, MBV)                                                                                           \
+    gemv4_fast_kernel<T, QT, MBV><<<g, kWarpsPerCta * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code,         \
+                                                                       absmax_offset, out, bias, M, N, K, ldc, l2)
+            if (quant_type == kNF4) {
+                if (M == 1) BNB200_FAST(kNF4, 1);
+                else if (M == 2) BNB200_FAST(kNF4, 2);
+                else if (M <= 4) BNB200_FAST(kNF4, 4);
+                else BNB200_FAST(kNF4, 8);
+            } else {
+                if (M == 1) BNB200_FAST(kFP4, 1);
+                else if (M == 2) BNB200_FAST(kFP4, 2);
+                else if (M <= 4) BNB200_FAST(kFP4, 4);
+                else BNB200_FAST(kFP4, 8);
+            }
+#undef BNB200_FAST
+            BNB200_CHECK_LAUNCH("gemv4_fast");
+            return;
+        }
+    }
     const bool vec_ok = (K % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(B) & 3) == 0) && (blocksize % 8 == 0);
     dim3 grid((N + kWarpsPerCta - 1) / kWarpsPerCta, (M + kMB - 1) / kMB);

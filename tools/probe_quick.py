@@ -11,5 +11,14 @@ if len(sys.argv) > 1:
 for (M, N, K) in shapes:
     p = make_problem(M, N, K, "nf4", "bf16")
     t, t0 = timeit(lambda: run_nosync(nat.lib, p), iters=15)
-    print(f"{M}x{N}x{K}: {t:.1f} us  {2.0 * M * N * K / t / 1e6:.1f} TFLOPS (min {t0:.1f})", flush=True)
+    extra = ""
+    if M <= 16:
+        nat.lib.cbnb_b200_gemm_4bit_force_path(0)
+        ts, ts0 = timeit(lambda: run_nosync(nat.lib, p), iters=15)
+        nat.lib.cbnb_b200_gemm_4bit_force_path(1)
+        tt, tt0 = timeit(lambda: run_nosync(nat.lib, p), iters=15)
+        nat.lib.cbnb_b200_gemm_4bit_force_path(-1)
+        tn, _ = timeit(lambda: run_nosync(nat.lib, p), iters=15, flush=False)
+        extra = f" | simt {ts:.1f} (min {ts0:.1f})  tc {tt:.1f} (min {tt0:.1f})  auto-noflush {tn:.1f}"
+    print(f"{M}x{N}x{K}: {t:.1f} us  {2.0 * M * N * K / t / 1e6:.1f} TFLOPS (min {t0:.1f}){extra}", flush=True)
 nat.check()

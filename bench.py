@@ -170,8 +170,19 @@ def cpu_reference(N, K, M_total, qt, packed_u8, absmax_f32, x_bf16_cpu, budget_s
 
 
 # ------------------------------------------------------------------------------------------ main
+def _protect_stdout():
+    """Native libraries (NCCL's version banner, cuBLAS warnings) write to file descriptor 1; the
+    driver wants exactly one JSON line there.  Point fd 1 at stderr and keep Python's sys.stdout
+    on the original descriptor."""
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+
+
 def main():
     args = parse_args()
+    _protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

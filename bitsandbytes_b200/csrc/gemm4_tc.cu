@@ -63,7 +63,11 @@ struct Gemm4Params {
     int M, N, K, ldc;
     int log2_bs;
     int kblocks_total;           // number of 128-wide stages = ceil(K / 128)
-    int kblocks_per_split;
+    int kblocks_per_split;       // unused by the kernel (kept for bookkeeping)
+    int n_tiles;                 // N tiles of 128 (tile = m_tile * n_tiles + n_tile)
+    int tiles_total;
+    int tiles_main;              // tiles [0, tiles_main) run with `splits` K-splits, the rest (the partial last
+    int splits_tail;             //   wave) with `splits_tail` K-splits so that it fills the machine
     int splits;
     int debug;                   // developer knobs (BNB_B200_DEBUG): 1 skip decode math, 2 skip tcgen05.st, 4 skip TMA, 8 skip MMA
 };
@@ -112,17 +116,33 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint64_t* w_full = bars + 2 * kStages;   // [kStages] TMA (1 arrive + W bytes) -> decode warps
     uint64_t* acc_full = bars + 3 * kStages; // MMA -> epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
-    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int n0 = blockIdx.x * kTileN;
-    const int m0 = blockIdx.y * MT;
-    const int split = blockIdx.z;
-    // work is split in 128-wide stages; kb64_* count 64-wide k-blocks
-    const int st_begin = split * p.kblocks_per_split;
-    int st_end = st_begin + p.kblocks_per_split;
+    // Linear CTA id -> (tile, K-split).  Within a region the ids are ordered
+    // (tile group of CL tiles, split, tile in group) so that a cluster = CL consecutive ids shares
+    // the m-tile and the split and covers CL consecutive n-tiles.
+    int lin = blockIdx.x;
+    int splits = p.splits, tile_base = 0, slot_base = 0;
+    const int main_ctas = p.tiles_main * p.splits;
+    if (lin >= main_ctas) {
+        lin -= main_ctas;
+        splits = p.splits_tail;
+        tile_base = p.tiles_main;
+        slot_base = p.splits > 1 ? main_ctas : 0;
+    }
+    const int tg = lin / (splits * CL);
+    const int rem = lin - tg * (splits * CL);
+    const int split = rem / CL;
+    const int tile_id = tile_base + tg * CL + (rem - split * CL);
+    const int slot0 = slot_base + (tile_id - tile_base) * splits;  // first workspace slot of this tile
+    const int n0 = (tile_id % p.n_tiles) * kTileN;
+    const int m0 = (tile_id / p.n_tiles) * MT;
+    // work is split in 128-wide stages
+    const int per = (p.kblocks_total + splits - 1) / splits;
+    const int st_begin = split * per;
+    int st_end = st_begin + per;
     if (st_end > p.kblocks_total) st_end = p.kblocks_total;
     const int nst = st_end - st_begin;  // >= 1 by construction
     const int kb64_total = p.K / 64;    // the last stage may hold a single 64-wide block
@@ -332,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         float bias_v = 0.f;
         if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
 
-        if (p.splits == 1) {
+        if (splits == 1) {
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += kChunk) {
                 uint32_t v[32];
@@ -353,9 +373,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
         } else {
-            // ---- split-K: publish the fp32 partial, last arriver reduces in split order
-            const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-            float* my = p.ws_partial + ((long long)(tile_id * p.splits + split) * kTileN + row) * MT;
+            // ---- split-K: every split CTA publishes its fp32 partial tile (layout [column m][row n], so
+            // that both the write and the later reads are 128-byte coalesced), the splits of a tile
+            // rendezvous on a counter, and EACH of them then reduces a 1/splits share of the columns
+            // (in split order: deterministic).  All split CTAs of a tile are resident at the same time
+            // by construction (the split grid never exceeds one wave), so the short spin cannot deadlock.
+            float* ws_tile = p.ws_partial + (long long)slot0 * kTileN * MT;
+            float* my = ws_tile + (long long)split * kTileN * MT;
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += kChunk) {
                 uint32_t v[32];
@@ -369,39 +393,41 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 ptx::tmem_wait_ld();
 #pragma unroll
-                for (int t = 0; t < kChunk; t += 4) {
-                    *reinterpret_cast<uint4*>(my + col0 + c + t) = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-                }
+                for (int t = 0; t < kChunk; ++t) my[(col0 + c + t) * kTileN + row] = __uint_as_float(v[t]);
             }
             __threadfence();
-            // named barrier over the 8 epilogue warps (256 threads); barrier 0 is __syncthreads
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            int* arrive = p.ws_counter + tile_id;
+            int* done = p.ws_counter + p.tiles_total + tile_id;
             if (threadIdx.x == 64) {
-                int prev = atomicAdd(p.ws_counter + tile_id, 1);
-                *s_flag = (prev == p.splits - 1) ? 1 : 0;
-                if (prev == p.splits - 1) p.ws_counter[tile_id] = 0;  // self-reset for the next launch
+                atomicAdd(arrive, 1);
+                while (atomicAdd(arrive, 0) < splits) __nanosleep(64);
+                __threadfence();
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (*s_flag) {
-                __threadfence();
-                const float* base = p.ws_partial + ((long long)(tile_id * p.splits) * kTileN + row) * MT;
-#pragma unroll 1
-                for (int c = 0; c < kColsPerWarp; c += 4) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int sp = 0; sp < p.splits; ++sp) {
-                        const float4 x = __ldcg(reinterpret_cast<const float4*>(
-                            base + (long long)sp * kTileN * MT + col0 + c));
-                        acc.x += x.x;
-                        acc.y += x.y;
-                        acc.z += x.z;
-                        acc.w += x.w;
-                    }
-                    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int m = m0 + col0 + c + t;
-                        if (n_ok && m < p.M) outp[(long long)m * p.ldc + n] = DT<T>::from_f32(a4[t] + bias_v);
-                    }
+            {
+                const int e = threadIdx.x - 64;          // 0..511 over the 16 epilogue warps
+                const int rn = e & (kTileN - 1);         // output feature inside the tile
+                const int cg = e >> 7;                   // 0..3
+                const int nn = n0 + rn;
+                float bias_r = 0.f;
+                if (p.bias != nullptr && nn < p.N) bias_r = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[nn]);
+                for (int c = split + splits * cg; c < MT; c += splits * 4) {
+                    const int m = m0 + c;
+                    if (m >= p.M) break;
+                    float acc = 0.f;
+                    for (int sp = 0; sp < splits; ++sp)
+                        acc += __ldcg(ws_tile + ((long long)sp * MT + c) * kTileN + rn);
+                    if (nn < p.N) outp[(long long)m * p.ldc + nn] = DT<T>::from_f32(acc + bias_r);
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (threadIdx.x == 64) {
+                // last split out resets the tile's counters for the next launch
+                if (atomicAdd(done, 1) == splits - 1) {
+                    *arrive = 0;
+                    *done = 0;
+                    __threadfence();
                 }
             }
         }
@@ -492,6 +518,15 @@ Workspace* get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_cou
     return &e->ws;
 }
 
+int tail_split_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BNB_B200_TAIL_SPLIT");
+        v = e ? atoi(e) : 0;  // measured: helps 2048x14336x4096 (219 -> 208 us), hurts 4096^3 (131 -> 141 us)
+    }
+    return v;
+}
+
 int cluster_override() {
     static int v = -2;
     if (v == -2) {
@@ -524,26 +559,74 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     const int n_tiles = (p.N + kTileN - 1) / kTileN;
     const int m_tiles = (p.M + MT - 1) / MT;
 
-    // split-K so that small problems still cover the machine in one wave, >= 4 k-blocks per split
-    const int sms = device_sm_count();
-    int splits = 1;
-    const int tiles = n_tiles * m_tiles;
-    if (tiles * 2 <= sms) {
-        splits = sms / tiles;
-        int max_by_k = p.kblocks_total / 2;  // >= two 128-wide stages per split
-        if (max_by_k < 1) max_by_k = 1;
-        if (splits > max_by_k) splits = max_by_k;
-        if (splits > 16) splits = 16;
+    // K-splitting.  (a) small problems: a uniform split so that one wave covers the machine;
+    // (b) large problems: full tiles for the whole waves, and the partial LAST wave split along K
+    // so that it also fills the machine ("tail split": 4096^3 has 512 tiles = 3.46 waves of 148;
+    // the last 68 tiles run as 136 half-K CTAs and cost half a wave instead of a full one).
+    // Split CTAs exchange fp32 partials through an L2-resident workspace (last arriver reduces,
+    // in split order).  Every region size is a multiple of the cluster size.
+    // CTAs that can be resident at once: SM count for CL == 1; for clusters the hardware may strand a
+    // few SMs (GPC granularity), so ask the occupancy API.
+    static int wave_ctas = 0;
+    if (wave_ctas == 0) {
+        wave_ctas = device_sm_count();
+        if (CL > 1) {
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = dim3(CL * 64, 1, 1);
+            qc.blockDim = dim3(kThreads);
+            qc.dynamicSmemBytes = smem_bytes;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CL;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa;
+            qc.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &qc) == cudaSuccess && nclusters > 0) {
+                wave_ctas = nclusters * CL;
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
     }
-    int per = (p.kblocks_total + splits - 1) / splits;
-    splits = (p.kblocks_total + per - 1) / per;  // no empty split
+    const int sms = wave_ctas;
+    const int tiles = n_tiles * m_tiles;
+    const int max_by_k = p.kblocks_total / 2 > 0 ? p.kblocks_total / 2 : 1;  // >= two 128-wide stages per split
+    auto clamp_splits = [&](int v) {
+        if (v > max_by_k) v = max_by_k;
+        if (v > 16) v = 16;
+        if (v < 1) v = 1;
+        const int per = (p.kblocks_total + v - 1) / v;
+        return (p.kblocks_total + per - 1) / per;  // no empty split
+    };
+    int splits = 1, splits_tail = 1, tiles_main = tiles;
+    if (tiles * 2 <= sms) {
+        splits = clamp_splits(sms / tiles);
+    } else if (tiles > sms && tail_split_enabled()) {
+        int full = (tiles / sms) * sms;
+        full -= full % CL;
+        const int rest = tiles - full;
+        if (rest > 0 && rest * 2 <= sms) {
+            const int st = clamp_splits(sms / rest);
+            if (st > 1) {
+                tiles_main = full;
+                splits_tail = st;
+            }
+        }
+    }
     p.splits = splits;
-    p.kblocks_per_split = per;
+    p.splits_tail = splits_tail;
+    p.tiles_main = tiles_main;
+    p.n_tiles = n_tiles;
+    p.tiles_total = tiles;
+    p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
     p.ws_partial = nullptr;
     p.ws_counter = nullptr;
-    if (splits > 1) {
-        size_t bytes = size_t(tiles) * splits * kTileN * MT * sizeof(float);
-        Workspace* ws = get_workspace(stream, bytes, tiles);
+    const int split_slots = (splits > 1 ? tiles_main * splits : 0) + (splits_tail > 1 ? (tiles - tiles_main) * splits_tail : 0);
+    if (split_slots > 0) {
+        size_t bytes = size_t(split_slots) * kTileN * MT * sizeof(float);
+        Workspace* ws = get_workspace(stream, bytes, 2 * (size_t)tiles);
         if (ws == nullptr) {
             set_last_error_msg("gemm4_tc: could not allocate the split-K workspace");
             return false;
@@ -551,8 +634,9 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
         p.ws_partial = reinterpret_cast<float*>(ws->ptr);
         p.ws_counter = ws->counters;
     }
+    const int grid_ctas = tiles_main * splits + (tiles - tiles_main) * splits_tail;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tiles, m_tiles, splits);
+    cfg.gridDim = dim3(grid_ctas, 1, 1);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
@@ -618,11 +702,10 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     // Cluster of CL n-tiles sharing one activation tile by TMA multicast: only worth it when the
     // activation tile is the dominant L2 traffic (large M) and the n-tile count divides.
     const int n_tiles = (N + kTileN - 1) / kTileN;
+    // Measured on B200 (round 1): multicast does not pay yet -- the kernel is decode(ALU)-bound, not
+    // L2-bound, and clusters of 4 strand 16 of the 148 SMs -- so the default is CL = 1
+    // (4096^3: 131 us with CL=1, 136 us with CL=2, 138 us with CL=4).  BNB_B200_CLUSTER=2|4 enables it.
     int CL = 1;
-    if (MT >= 128) {
-        if (n_tiles % 4 == 0) CL = 4;
-        else if (n_tiles % 2 == 0) CL = 2;
-    }
     const int ov = cluster_override();
     if (ov == 1 || (ov == 2 && n_tiles % 2 == 0 && MT >= 128) || (ov == 4 && n_tiles % 4 == 0 && MT >= 128)) CL = ov;
 

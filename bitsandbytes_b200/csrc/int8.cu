@@ -434,12 +434,22 @@ void launch_dequant_mm_int32_fp16(const int* A, const float* rowStats, const flo
     BNB200_CHECK_LAUNCH("dequant_mm_int32_fp16");
 }
 
+// int8_persist.cu (experimental persistent / multicast variant)
+int launch_int8_gemm_persistent(const int8_t* acts, const int8_t* weights, void* out, const float* SCA,
+                                const float* SCB, const void* bias, int M, int N, int K, int ldc, int epi,
+                                cudaStream_t stream);
+
 // epi: 0 int32, 1 fp16, 2 bf16.  Returns 0 ok, 100 "not implemented for this shape".
 int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const float* SCA, const float* SCB,
                      const void* bias, int M, int N, int K, int ldc, int epi, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (K % 16) != 0) return 100;
     if ((reinterpret_cast<uintptr_t>(acts) & 15) != 0 || (reinterpret_cast<uintptr_t>(weights) & 15) != 0) return 100;
+    static const bool persistent = [] {
+        const char* e = getenv("BNB_B200_I8_PERSISTENT");
+        return e != nullptr && e[0] == '1';
+    }();
+    if (persistent) return launch_int8_gemm_persistent(acts, weights, out, SCA, SCB, bias, M, N, K, ldc, epi, stream);
     CUtensorMap ta, tb;
     if (!encode_tmap_2d(&ta, acts, 1, 128, (uint64_t)M, (uint64_t)K, (uint64_t)K, kI8TileM, kI8BK)) return 100;
     if (!encode_tmap_2d(&tb, weights, 1, 128, (uint64_t)N, (uint64_t)K, (uint64_t)K, kI8TileN, kI8BK))

@@ -1,0 +1,362 @@
+// int8_persist.cu -- persistent, cluster-multicast variant of the tcgen05 int8 GEMM in int8.cu.
+//
+// Experimental: selected with BNB_B200_I8_PERSISTENT=1 (launch_int8_gemm in int8.cu), off by
+// default until it is parity-green and faster than the one-tile-per-CTA kernel on the B200.
+// Same contract as int8.cu's GEMM (reference igemmlt<32,0>, csrc/ops.cu:282-404, plus the fused
+// kdequant_mm_int32_fp16 epilogue, csrc/kernels.cu:1396-1448).
+#include <cstdio>
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace bnb200 {
+
+namespace {
+
+constexpr float kMmDequantConst = 6.200012e-05f;  // reference kernels.cu:1394 ("1/(127*127)")
+
+__device__ __forceinline__ float dequant_value(int acc, float rs, float cs, float bias) {
+    // reference kernels.cu:1436-1438: fmaf(int * rowStats * colStats, C, bias), all ftz
+    float t = mul_ftz(mul_ftz((float)acc, rs), cs);
+    float r;
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(t), "f"(kMmDequantConst), "f"(bias));
+    return r;
+}
+
+// ======================================================================================
+// tcgen05 int8 GEMM:  C[M,N] = A[M,K] . B[N,K]^T   (A = activations, B = weights)
+//
+// Persistent, warp-specialised, 2-CTA clusters:
+//   * tile 128 (tokens, TMEM lanes) x 256 (features, TMEM columns), K in 128-byte stages,
+//     4-stage TMA ring (128-byte swizzle), int32 accumulators in TMEM;
+//   * the two CTAs of a cluster work on vertically adjacent m-tiles of the SAME n-tile: each
+//     fetches half of the 256-row weight tile and MULTICASTS it to both -- the int8 GEMM at
+//     8192 MAC/cycle/SM is L2-bandwidth-bound with unshared 128x256 tiles (94 B/cycle/SM);
+//   * accumulators are double-buffered (2 x 256 TMEM columns): four epilogue warps drain tile t
+//     (tcgen05.ld -> dequantise -> store) while the MMA warp already accumulates tile t+1;
+//   * static persistent schedule: cluster c processes tile pairs c, c + #clusters, ...
+// ======================================================================================
+constexpr int kI8Stages = 4;
+constexpr int kI8BK = 128;        // int8 elements per stage = one 128-byte swizzled row
+constexpr int kI8TileM = 128;     // tokens per CTA tile (TMEM lanes)
+constexpr int kI8TileN = 256;     // output features per CTA tile (TMEM columns)
+constexpr int kI8Threads = 6 * 32;
+constexpr int kI8ABytes = kI8TileM * 128;
+constexpr int kI8BBytes = kI8TileN * 128;
+constexpr int kI8StageBytes = kI8ABytes + kI8BBytes;
+constexpr int kI8Cluster = 2;
+
+// Watchdog waits (debug builds of this experimental kernel): a wait that does not complete within
+// 2 s reports itself once and releases every other wait, so a protocol bug ends the kernel with a
+// diagnostic instead of hanging the device.
+#ifndef I8P_WATCHDOG
+#define I8P_WATCHDOG 1
+#endif
+#if I8P_WATCHDOG
+__device__ int g_i8p_abort = 0;
+__device__ int g_i8p_reports = 0;
+#endif
+
+__device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, int a, int b) {
+#if I8P_WATCHDOG
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFF) == 0) {
+            if (*reinterpret_cast<volatile int*>(&g_i8p_abort) != 0) return;
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > 2000000000ull) {
+                if ((threadIdx.x & 31) == 0 && atomicAdd(&g_i8p_reports, 1) < 48)
+                    printf("i8p TIMEOUT tag=%d block=%d warp=%d parity=%u a=%d b=%d\n", tag, (int)blockIdx.x,
+                           (int)(threadIdx.x >> 5), parity, a, b);
+                *reinterpret_cast<volatile int*>(&g_i8p_abort) = 1;
+                __threadfence();
+                return;
+            }
+        }
+    }
+#else
+    ptx::mbar_wait(bar, parity);
+#endif
+}
+
+// EPI: 0 = int32 out, 1 = fp16 out, 2 = bf16 out (fused dequant)
+struct I8Params {
+    void* out;
+    const float* SCA;   // [M]  row stats of the activations
+    const float* SCB;   // [N]  row stats of the weights
+    const void* bias;   // T[N] or NULL
+    int M, N, K, ldc;
+    int kblocks;
+    int n_tiles, m_pairs, pair_tiles;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kI8Threads, 1)
+    int8_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const I8Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = smem;
+    float* s_scb = reinterpret_cast<float*>(smem + kI8Stages * kI8StageBytes);   // [2][256]
+    float* s_bias = s_scb + 2 * kI8TileN;                                          // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kI8Stages * kI8StageBytes + 4096);
+    uint64_t* full = bars;                       // [stages] TMA -> MMA
+    uint64_t* empty = bars + kI8Stages;          // [stages] MMA of both cluster CTAs -> TMA
+    uint64_t* tmem_full = bars + 2 * kI8Stages;  // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;        // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 512;
+    constexpr uint16_t kMask = (uint16_t)((1u << kI8Cluster) - 1u);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < kI8Stages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], kI8Cluster);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<kTmemCols>(tmem_slot);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x / kI8Cluster;
+    const int n_clusters = gridDim.x / kI8Cluster;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters) {
+                const int n0 = (pt % p.n_tiles) * kI8TileN;
+                const int m0 = ((pt / p.n_tiles) * kI8Cluster + (int)rank) * kI8TileM;
+                for (int i = 0; i < p.kblocks; ++i, ++it) {
+                    const int s = it % kI8Stages;
+                    const uint32_t ph = (it / kI8Stages) & 1u;
+                    wait_wd(&empty[s], ph ^ 1u, 1, (int)it, pt);
+                    ptx::mbar_arrive_expect_tx(&full[s], kI8StageBytes);
+                    uint8_t* sa = stages + s * kI8StageBytes;
+                    ptx::tma_load_2d(sa, &tmap_a, &full[s], i * kI8BK, m0);
+                    // my half of the weight tile, to both CTAs
+                    ptx::tma_load_2d_multicast(sa + kI8ABytes + rank * (kI8BBytes / kI8Cluster), &tmap_b, &full[s],
+                                               i * kI8BK, n0 + (int)rank * (kI8TileN / kI8Cluster), kMask);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        // kind::i8: D = S32 (2), A/B = signed int8 (1); UMMA K = 32 bytes
+        constexpr uint32_t idesc = ptx::make_idesc(2, 1, 1, kI8TileM, kI8TileN);
+        uint32_t it = 0, tcount = 0;
+        for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
+            const uint32_t acc = tcount & 1u;
+            wait_wd(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);  // epilogue has drained this accumulator
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kI8TileN;
+            for (int i = 0; i < p.kblocks; ++i, ++it) {
+                const int s = it % kI8Stages;
+                const uint32_t ph = (it / kI8Stages) & 1u;
+                wait_wd(&full[s], ph, 3, (int)it, pt);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = ptx::smem_u32(stages + s * kI8StageBytes);
+                    const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + kI8ABytes);
+#pragma unroll
+                    for (int j = 0; j < kI8BK / 32; ++j)
+                        ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
+                    ptx::tc_commit_multicast(&empty[s], kMask);
+                    if (i == p.kblocks - 1) ptx::tc_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================== epilogue warps 2..5
+        const int quarter = warp & 3;  // TMEM lane quarter
+        const int et = threadIdx.x - 64;  // 0..127
+        uint32_t tcount = 0;
+        for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
+            const uint32_t acc = tcount & 1u;
+            const int n0 = (pt % p.n_tiles) * kI8TileN;
+            const int m0 = ((pt / p.n_tiles) * kI8Cluster + (int)rank) * kI8TileM;
+            const int m = m0 + quarter * 32 + lane;
+            const bool m_ok = m < p.M;
+            float* scb = s_scb + acc * kI8TileN;
+            float* sbias = s_bias + acc * kI8TileN;
+            if (EPI != 0) {
+                // this buffer was last read two tiles ago by these same warps (ordered by the named
+                // barrier of the previous use)
+                for (int c = et; c < kI8TileN; c += 128) {
+                    const int n = n0 + c;
+                    scb[c] = (n < p.N) ? __ldg(p.SCB + n) : 0.f;
+                    float b = 0.f;
+                    if (p.bias != nullptr && n < p.N) {
+                        if (EPI == 1)
+                            b = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+                        else
+                            b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+                    }
+                    sbias[c] = b;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float sca = 0.f;
+            if (EPI != 0 && m_ok) sca = __ldg(p.SCA + m);
+            wait_wd(&tmem_full[acc], (tcount >> 1) & 1u, 4, (int)tcount, pt);
+            ptx::tc_fence_after();
+            const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * kI8TileN;
+#pragma unroll 1
+            for (int c = 0; c < kI8TileN; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(lane_addr + c, v);
+                ptx::tmem_wait_ld();
+                if (c + 32 == kI8TileN) {
+                    // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!m_ok) continue;
+                const int n = n0 + c;
+                if (EPI == 0) {
+                    int* dst = reinterpret_cast<int*>(p.out) + (long long)m * p.ldc + n;
+                    if (n + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int t = 0; t < 32; t += 4)
+                            *reinterpret_cast<uint4*>(dst + t) = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+                    } else {
+                        for (int t = 0; t < 32; ++t)
+                            if (n + t < p.N) dst[t] = (int)v[t];
+                    }
+                } else {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        if (EPI == 1) {
+                            const float f0 = dequant_value((int)v[t], sca, scb[c + t], sbias[c + t]);
+                            const float f1 = dequant_value((int)v[t + 1], sca, scb[c + t + 1], sbias[c + t + 1]);
+                            w[t >> 1] = pack2<__half>(f0, f1);
+                        } else {
+                            // bf16 output, bit-identical to the reference chain (backends/cuda/ops.py:186-210):
+                            // the kernel result is fp16, a non-fp16 bias is added by `out.add_(bias)` on the
+                            // fp16 tensor (fp32 add, one rounding to fp16), then `.to(bfloat16)`.
+                            float f0 = __half2float(__float2half_rn(dequant_value((int)v[t], sca, scb[c + t], 0.f)));
+                            float f1 = __half2float(
+                                __float2half_rn(dequant_value((int)v[t + 1], sca, scb[c + t + 1], 0.f)));
+                            if (p.bias != nullptr) {
+                                f0 = __half2float(__float2half_rn(f0 + sbias[c + t]));
+                                f1 = __half2float(__float2half_rn(f1 + sbias[c + t + 1]));
+                            }
+                            w[t >> 1] = pack2<__nv_bfloat16>(f0, f1);
+                        }
+                    }
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldc + n;
+                    if (n + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int t = 0; t < 16; t += 4)
+                            *reinterpret_cast<uint4*>(dst + 2 * t) = make_uint4(w[t], w[t + 1], w[t + 2], w[t + 3]);
+                    } else {
+                        for (int t = 0; t < 32; ++t)
+                            if (n + t < p.N) dst[t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
+                    }
+                }
+            }
+            if (EPI != 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // scale buffers free for tile t+2
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // no CTA exits while its peer can still multicast into / arrive on its smem
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
+    }
+}
+
+template <int EPI> int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
+    constexpr size_t smem_bytes = 1024 + size_t(kI8Stages) * kI8StageBytes + 4096 + 256;
+    static bool attr_set = false;
+    auto kern = int8_gemm_tc_kernel<EPI>;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+            set_last_error("int8_gemm_tc smem attr", cudaGetLastError());
+            return 1;
+        }
+        attr_set = true;
+    }
+    p.n_tiles = (p.N + kI8TileN - 1) / kI8TileN;
+    const int m_tiles = (p.M + kI8TileM - 1) / kI8TileM;
+    p.m_pairs = (m_tiles + kI8Cluster - 1) / kI8Cluster;
+    p.pair_tiles = p.n_tiles * p.m_pairs;
+    int clusters = device_sm_count() / kI8Cluster;
+    if (clusters > p.pair_tiles) clusters = p.pair_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * kI8Cluster, 1, 1);
+    cfg.blockDim = dim3(kI8Threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kI8Cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_last_error("int8_gemm_tc launch", e);
+        return 1;
+    }
+    BNB200_CHECK_LAUNCH("int8_gemm_tc");
+    return 0;
+}
+
+} // namespace
+
+// epi: 0 int32, 1 fp16, 2 bf16.  Returns 0 ok, 100 "not implemented for this shape".
+int launch_int8_gemm_persistent(const int8_t* acts, const int8_t* weights, void* out, const float* SCA,
+                                const float* SCB, const void* bias, int M, int N, int K, int ldc, int epi,
+                                cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return 0;
+    if (K <= 0 || (K % 16) != 0) return 100;
+    if ((reinterpret_cast<uintptr_t>(acts) & 15) != 0 || (reinterpret_cast<uintptr_t>(weights) & 15) != 0) return 100;
+    CUtensorMap ta, tb;
+    if (!encode_tmap_2d(&ta, acts, 1, 128, (uint64_t)M, (uint64_t)K, (uint64_t)K, kI8TileM, kI8BK)) return 100;
+    if (!encode_tmap_2d(&tb, weights, 1, 128, (uint64_t)N, (uint64_t)K, (uint64_t)K, kI8TileN / kI8Cluster, kI8BK))
+        return 100;
+    I8Params p{};
+    p.out = out;
+    p.SCA = SCA;
+    p.SCB = SCB;
+    p.bias = bias;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.ldc = ldc;
+    p.kblocks = (K + kI8BK - 1) / kI8BK;
+    switch (epi) {
+    case 0: return launch_i8<0>(ta, tb, p, stream);
+    case 1: return launch_i8<1>(ta, tb, p, stream);
+    default: return launch_i8<2>(ta, tb, p, stream);
+    }
+}
+
+} // namespace bnb200

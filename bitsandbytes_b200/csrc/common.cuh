@@ -27,6 +27,18 @@ __device__ __forceinline__ float mul_ftz(float a, float b) {
     return r;
 }
 
+// LLM.int8() dequantisation of one int32 accumulator (shared by the stand-alone kernel in int8.cu
+// and the fused GEMM epilogue in int8_gemm.cu).
+constexpr float kMmDequantConst = 6.200012e-05f;  // reference kernels.cu:1394 ("1/(127*127)")
+
+__device__ __forceinline__ float dequant_value(int acc, float rs, float cs, float bias) {
+    // reference kernels.cu:1436-1438: fmaf(int * rowStats * colStats, C, bias), all ftz
+    float t = mul_ftz(mul_ftz((float)acc, rs), cs);
+    float r;
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(t), "f"(kMmDequantConst), "f"(bias));
+    return r;
+}
+
 __device__ __forceinline__ float rcp_approx_ftz(float a) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));

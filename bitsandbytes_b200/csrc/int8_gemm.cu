@@ -1,9 +1,11 @@
-// int8_persist.cu -- persistent, cluster-multicast variant of the tcgen05 int8 GEMM in int8.cu.
+// int8_gemm.cu -- the LLM.int8() GEMM for sm_100a:  C[M,N] = A[M,K] . B[N,K]^T, int8 x int8 -> int32.
 //
-// Experimental: selected with BNB_B200_I8_PERSISTENT=1 (launch_int8_gemm in int8.cu), off by
-// default until it is parity-green and faster than the one-tile-per-CTA kernel on the B200.
-// Same contract as int8.cu's GEMM (reference igemmlt<32,0>, csrc/ops.cu:282-404, plus the fused
-// kdequant_mm_int32_fp16 epilogue, csrc/kernels.cu:1396-1448).
+// Replaces reference igemmlt<32,0> -> cublasLtMatmul (csrc/ops.cu:282-404) with a tcgen05 kind::i8
+// kernel: both operands TMA-staged (128-byte swizzle), int32 accumulators in TMEM, exact.  The
+// epilogue either stores int32 (cigemmlt_32 ABI) or applies the dequantisation of reference
+// kdequant_mm_int32_fp16 (csrc/kernels.cu:1396-1448),
+//     fp16/bf16( fma(acc * SCA[m] * SCB[n], 1/127^2, bias[n]) ),
+// in-kernel, which removes the 2 x M x N x 4-byte int32 round trip through HBM.
 #include <cstdio>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -12,74 +14,58 @@ namespace bnb200 {
 
 namespace {
 
-constexpr float kMmDequantConst = 6.200012e-05f;  // reference kernels.cu:1394 ("1/(127*127)")
-
-__device__ __forceinline__ float dequant_value(int acc, float rs, float cs, float bias) {
-    // reference kernels.cu:1436-1438: fmaf(int * rowStats * colStats, C, bias), all ftz
-    float t = mul_ftz(mul_ftz((float)acc, rs), cs);
-    float r;
-    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(t), "f"(kMmDequantConst), "f"(bias));
-    return r;
-}
-
 // ======================================================================================
-// tcgen05 int8 GEMM:  C[M,N] = A[M,K] . B[N,K]^T   (A = activations, B = weights)
-//
-// Persistent, warp-specialised, 2-CTA clusters:
-//   * tile 128 (tokens, TMEM lanes) x 256 (features, TMEM columns), K in 128-byte stages,
-//     4-stage TMA ring (128-byte swizzle), int32 accumulators in TMEM;
-//   * the two CTAs of a cluster work on vertically adjacent m-tiles of the SAME n-tile: each
-//     fetches half of the 256-row weight tile and MULTICASTS it to both -- the int8 GEMM at
-//     8192 MAC/cycle/SM is L2-bandwidth-bound with unshared 128x256 tiles (94 B/cycle/SM);
+// Persistent, warp-specialised kernel on 2-CTA clusters (one CTA per SM, 74 clusters):
+//   * CTA tile 128 (tokens, TMEM lanes) x 256 (features, TMEM columns), K in 128-byte k-blocks,
+//     TMA ring (128-byte swizzle) filling 192 KB of shared memory;
+//   * the two CTAs of a cluster work on vertically adjacent token tiles of the SAME feature tile
+//     and split the 256-row weight tile between them (see PAIR below);
 //   * accumulators are double-buffered (2 x 256 TMEM columns): four epilogue warps drain tile t
 //     (tcgen05.ld -> dequantise -> store) while the MMA warp already accumulates tile t+1;
 //   * static persistent schedule: cluster c processes tile pairs c, c + #clusters, ...
+// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = epilogue.
 // ======================================================================================
-constexpr int kI8Stages = 4;
 constexpr int kI8BK = 128;        // int8 elements per stage = one 128-byte swizzled row
 constexpr int kI8TileM = 128;     // tokens per CTA tile (TMEM lanes)
 constexpr int kI8TileN = 256;     // output features per CTA tile (TMEM columns)
 constexpr int kI8Threads = 6 * 32;
 constexpr int kI8ABytes = kI8TileM * 128;
-constexpr int kI8BBytes = kI8TileN * 128;
-constexpr int kI8StageBytes = kI8ABytes + kI8BBytes;
 constexpr int kI8Cluster = 2;
+constexpr int kI8RingBytes = 192 * 1024;
 
-// Watchdog waits (debug builds of this experimental kernel): a wait that does not complete within
-// 2 s reports itself once and releases every other wait, so a protocol bug ends the kernel with a
-// diagnostic instead of hanging the device.
-#ifndef I8P_WATCHDOG
-#define I8P_WATCHDOG 1
-#endif
-#if I8P_WATCHDOG
-__device__ int g_i8p_abort = 0;
-__device__ int g_i8p_reports = 0;
-#endif
+// PAIR = true (default): one tcgen05.mma.cta_group::2 (M = 256) per CTA pair, issued by the leader;
+//               each CTA stages only ITS half of the weight tile and the tensor cores of both SMs
+//               read it.  Per 128-deep k-block every SM pulls 32 KB through L2 -> shared memory.
+// PAIR = false: one tcgen05.mma (cta_group::1, M = 128) per CTA; each CTA holds the whole 256-row
+//               weight tile, half of it fetched by its peer and multicast (48 KB into each SM).
+// Measured at 4096 x 11008 x 4096 (profiles/r01_int8_gemm_{pair,mc}.json): pair 135 us with 1.44 GB
+// crossing the L2 -> SM crossbar, multicast 140-151 us with 2.17 GB; tensor pipe 68 % active in both.
+template <bool PAIR> struct I8Cfg {
+    static constexpr int kBBytes = (PAIR ? kI8TileN / 2 : kI8TileN) * 128;
+    static constexpr int kStageBytes = kI8ABytes + kBBytes;
+    static constexpr int kStages = kI8RingBytes / kStageBytes;  // 4 x 48 KB or 6 x 32 KB
+};
 
+// Every mbarrier wait in this kernel is bounded: a wait that has not completed after 10 s (a protocol
+// bug, or a peer CTA that died) reports itself and traps, so the failure surfaces as a CUDA error at
+// the next synchronisation instead of a hung device.  The check costs one clock read per 16K polls.
 __device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, int a, int b) {
-#if I8P_WATCHDOG
     uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!ptx::mbar_try_wait(bar, parity)) {
         if ((++spins & 0x3FFF) == 0) {
-            if (*reinterpret_cast<volatile int*>(&g_i8p_abort) != 0) return;
             uint64_t now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) {
                 t0 = now;
-            } else if (now - t0 > 2000000000ull) {
-                if ((threadIdx.x & 31) == 0 && atomicAdd(&g_i8p_reports, 1) < 48)
-                    printf("i8p TIMEOUT tag=%d block=%d warp=%d parity=%u a=%d b=%d\n", tag, (int)blockIdx.x,
-                           (int)(threadIdx.x >> 5), parity, a, b);
-                *reinterpret_cast<volatile int*>(&g_i8p_abort) = 1;
-                __threadfence();
-                return;
+            } else if (now - t0 > 10000000000ull) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("int8_gemm: barrier wait timed out (tag=%d block=%d warp=%d parity=%u it=%d tile=%d)\n", tag,
+                           (int)blockIdx.x, (int)(threadIdx.x >> 5), parity, a, b);
+                __trap();
             }
         }
     }
-#else
-    ptx::mbar_wait(bar, parity);
-#endif
 }
 
 // EPI: 0 = int32 out, 1 = fp16 out, 2 = bf16 out (fused dequant)
@@ -93,13 +79,15 @@ struct I8Params {
     int n_tiles, m_pairs, pair_tiles;
 };
 
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(kI8Threads, 1)
     int8_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const I8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stages = smem;
+    constexpr int kI8Stages = I8Cfg<PAIR>::kStages;
+    constexpr int kI8StageBytes = I8Cfg<PAIR>::kStageBytes;
     float* s_scb = reinterpret_cast<float*>(smem + kI8Stages * kI8StageBytes);   // [2][256]
     float* s_bias = s_scb + 2 * kI8TileN;                                          // [2][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kI8Stages * kI8StageBytes + 4096);
@@ -119,17 +107,24 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         ptx::prefetch_tmap(&tmap_b);
         for (int s = 0; s < kI8Stages; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], kI8Cluster);
+            // multicast mode: the MMA threads of both CTAs release a stage; pair mode: one commit
+            ptx::mbar_init(&empty[s], PAIR ? 1 : kI8Cluster);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 4);
+            // pair mode: the leader's barrier collects the epilogue warps of both CTAs
+            ptx::mbar_init(&tmem_empty[a], PAIR ? 8 : 4);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc<kTmemCols>(tmem_slot);
-        ptx::tmem_relinquish();
+        if (PAIR) {
+            ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc<kTmemCols>(tmem_slot);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
@@ -150,21 +145,32 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                     const int s = it % kI8Stages;
                     const uint32_t ph = (it / kI8Stages) & 1u;
                     wait_wd(&empty[s], ph ^ 1u, 1, (int)it, pt);
-                    ptx::mbar_arrive_expect_tx(&full[s], kI8StageBytes);
                     uint8_t* sa = stages + s * kI8StageBytes;
-                    ptx::tma_load_2d(sa, &tmap_a, &full[s], i * kI8BK, m0);
-                    // my half of the weight tile, to both CTAs
-                    ptx::tma_load_2d_multicast(sa + kI8ABytes + rank * (kI8BBytes / kI8Cluster), &tmap_b, &full[s],
-                                               i * kI8BK, n0 + (int)rank * (kI8TileN / kI8Cluster), kMask);
+                    if (PAIR) {
+                        // both CTAs' boxes complete on the LEADER's barrier: it waits once per stage
+                        const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], kI8Cluster * kI8StageBytes);
+                        ptx::tma_load_2d_pair(sa, &tmap_a, lead_full, i * kI8BK, m0);
+                        ptx::tma_load_2d_pair(sa + kI8ABytes, &tmap_b, lead_full, i * kI8BK,
+                                              n0 + (int)rank * (kI8TileN / kI8Cluster));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[s], kI8StageBytes);
+                        ptx::tma_load_2d(sa, &tmap_a, &full[s], i * kI8BK, m0);
+                        // my half of the weight tile, to both CTAs
+                        ptx::tma_load_2d_multicast(sa + kI8ABytes + rank * (I8Cfg<PAIR>::kBBytes / kI8Cluster), &tmap_b,
+                                                   &full[s], i * kI8BK, n0 + (int)rank * (kI8TileN / kI8Cluster),
+                                                   kMask);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
         // kind::i8: D = S32 (2), A/B = signed int8 (1); UMMA K = 32 bytes
-        constexpr uint32_t idesc = ptx::make_idesc(2, 1, 1, kI8TileM, kI8TileN);
+        constexpr uint32_t idesc = ptx::make_idesc(2, 1, 1, PAIR ? 2 * kI8TileM : kI8TileM, kI8TileN);
         uint32_t it = 0, tcount = 0;
-        for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
+        // pair mode: only the leader issues; its instructions drive both SMs
+        for (int pt = (!PAIR || rank == 0) ? cluster_id : p.pair_tiles; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
             const uint32_t acc = tcount & 1u;
             wait_wd(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);  // epilogue has drained this accumulator
             ptx::tc_fence_after();
@@ -179,10 +185,19 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                     const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
                     const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + kI8ABytes);
 #pragma unroll
-                    for (int j = 0; j < kI8BK / 32; ++j)
-                        ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
-                    ptx::tc_commit_multicast(&empty[s], kMask);
-                    if (i == p.kblocks - 1) ptx::tc_commit(&tmem_full[acc]);
+                    for (int j = 0; j < kI8BK / 32; ++j) {
+                        if (PAIR)
+                            ptx::mma_i8_ss_pair(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
+                        else
+                            ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
+                    }
+                    if (PAIR) {
+                        ptx::tc_commit_pair(&empty[s], kMask);
+                        if (i == p.kblocks - 1) ptx::tc_commit_pair(&tmem_full[acc], kMask);
+                    } else {
+                        ptx::tc_commit_multicast(&empty[s], kMask);
+                        if (i == p.kblocks - 1) ptx::tc_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
             }
@@ -231,7 +246,12 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                     // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) {
+                        if (PAIR)
+                            ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty[acc]), 0));
+                        else
+                            ptx::mbar_arrive(&tmem_empty[acc]);
+                    }
                 }
                 if (!m_ok) continue;
                 const int n = n0 + c;
@@ -286,14 +306,18 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     ptx::cluster_sync();  // no CTA exits while its peer can still multicast into / arrive on its smem
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
+        if (PAIR)
+            ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+        else
+            ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
     }
 }
 
-template <int EPI> int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
-    constexpr size_t smem_bytes = 1024 + size_t(kI8Stages) * kI8StageBytes + 4096 + 256;
+template <int EPI, bool PAIR>
+int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
+    constexpr size_t smem_bytes = 1024 + size_t(I8Cfg<PAIR>::kStages) * I8Cfg<PAIR>::kStageBytes + 4096 + 256;
     static bool attr_set = false;
-    auto kern = int8_gemm_tc_kernel<EPI>;
+    auto kern = int8_gemm_tc_kernel<EPI, PAIR>;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("int8_gemm_tc smem attr", cudaGetLastError());
@@ -332,7 +356,7 @@ template <int EPI> int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I
 } // namespace
 
 // epi: 0 int32, 1 fp16, 2 bf16.  Returns 0 ok, 100 "not implemented for this shape".
-int launch_int8_gemm_persistent(const int8_t* acts, const int8_t* weights, void* out, const float* SCA,
+int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const float* SCA,
                                 const float* SCB, const void* bias, int M, int N, int K, int ldc, int epi,
                                 cudaStream_t stream) {
     if (M <= 0 || N <= 0) return 0;
@@ -352,10 +376,22 @@ int launch_int8_gemm_persistent(const int8_t* acts, const int8_t* weights, void*
     p.K = K;
     p.ldc = ldc;
     p.kblocks = (K + kI8BK - 1) / kI8BK;
+    // BNB_B200_I8_MODE=multicast selects the cta_group::1 variant (A/B measurements); default = pair
+    static const bool pair = [] {
+        const char* e = getenv("BNB_B200_I8_MODE");
+        return !(e != nullptr && e[0] == 'm');
+    }();
+    if (pair) {
+        switch (epi) {
+        case 0: return launch_i8<0, true>(ta, tb, p, stream);
+        case 1: return launch_i8<1, true>(ta, tb, p, stream);
+        default: return launch_i8<2, true>(ta, tb, p, stream);
+        }
+    }
     switch (epi) {
-    case 0: return launch_i8<0>(ta, tb, p, stream);
-    case 1: return launch_i8<1>(ta, tb, p, stream);
-    default: return launch_i8<2>(ta, tb, p, stream);
+    case 0: return launch_i8<0, false>(ta, tb, p, stream);
+    case 1: return launch_i8<1, false>(ta, tb, p, stream);
+    default: return launch_i8<2, false>(ta, tb, p, stream);
     }
 }
 

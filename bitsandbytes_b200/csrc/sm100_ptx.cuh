@@ -180,6 +180,68 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint
                  : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// A pair = the two CTAs of a 2-CTA cluster (same TPC).  One tcgen05.mma issued by the leader
+// (cluster rank 0) drives the tensor cores of both SMs: M = 256 (128 TMEM lanes in each CTA),
+// each CTA contributes its own 128 rows of A and its own half of the B tile from its own
+// shared memory, so every operand byte is read from shared memory once per pair.
+
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+
+// arrive on an mbarrier anywhere in the cluster (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// TMA load into this CTA's shared memory whose complete_tx lands on an mbarrier that may live in
+// the peer CTA of the pair (`bar_cluster_addr` from mapa_u32) -- the leader waits once for both halves.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+
+template <int kCols> __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// all prior tcgen05 ops of the pair -> arrive on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+// D[tmem, both CTAs] (+)= A[smem desc, per CTA] * B[smem desc, half per CTA]   (kind::i8, M = 256)
+__device__ __forceinline__ void mma_i8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                 "}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+
 // registers -> TMEM: thread t of the warp writes 16 consecutive 32-bit columns of lane
 // (32 * (warp_id % 4) + t).
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {

@@ -1,6 +1,6 @@
-"""Debug driver for the experimental persistent int8 GEMM (BNB_B200_I8_PERSISTENT=1)."""
+"""Correctness + timing driver for the int8 GEMM variants.  usage: debug_i8p.py [pair|multicast]"""
 import os, sys
-os.environ["BNB_B200_I8_PERSISTENT"] = "1"
+os.environ["BNB_B200_I8_MODE"] = sys.argv[1] if len(sys.argv) > 1 else "pair"
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import _native as nat
@@ -37,5 +37,5 @@ if ok:
         t1, _ = timeit(lambda: nat.lib.cigemmlt_32(None, N, M, K, CB.data_ptr(), CA.data_ptr(), C.data_ptr(), None, K, K, N, nat.stream()), iters=10)
         t2, _ = timeit(lambda: nat.lib.cbnb_b200_int8_scaled_mm(CA.data_ptr(), CB.data_ptr(), SCA.data_ptr(), SCB.data_ptr(), None, o16.data_ptr(), M, N, K, 1, nat.stream()), iters=10)
         t3, _ = timeit(lambda: torch._int_mm(CA, CB.t()), iters=10)
-        print(f"PERSISTENT M{M} K{K} N{N}: i32 {t1:.1f} us ({ops/t1/1e6:.0f} TOPS) | fused {t2:.1f} us ({ops/t2/1e6:.0f} TOPS) | cublasLt _int_mm {t3:.1f} us ({ops/t3/1e6:.0f} TOPS)", flush=True)
+        print(f"mode={os.environ['BNB_B200_I8_MODE']} M{M} K{K} N{N}: i32 {t1:.1f} us ({ops/t1/1e6:.0f} TOPS) | fused {t2:.1f} us ({ops/t2/1e6:.0f} TOPS) | cublasLt _int_mm {t3:.1f} us ({ops/t3/1e6:.0f} TOPS)", flush=True)
 print("done ok=", ok, flush=True)

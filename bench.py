@@ -270,6 +270,16 @@ def main():
             ev[i + 1].record()
         barrier()
         t_wall = time.perf_counter() - t_wall
+        # At the default K the timed region (~0.3 s) is shorter than a couple of nvidia-smi polls: keep
+        # the SAME load running, untimed, until the sampler holds a handful of readings under load.
+        t_stop = time.perf_counter() + 2.5
+        j = 0
+        while len(clocks.samples) < 6 and time.perf_counter() < t_stop:
+            for _ in range(64):
+                step(j)
+                j += 1
+            torch.cuda.synchronize()
+        clock_extra_steps = j
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     kernel_ms = sum(per_launch_ms) / len(per_launch_ms)
@@ -379,7 +389,7 @@ def main():
         "gpu_launches": args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "clocks": clocks.summary(),
+        "clocks": dict(clocks.summary(), window=f"timed region + {clock_extra_steps} untimed steps of the same loop"),
         "wall_s": t_wall,
     }
     print(json.dumps(line), flush=True)

@@ -6,7 +6,6 @@
 // kdequant_mm_int32_fp16 (csrc/kernels.cu:1396-1448),
 //     fp16/bf16( fma(acc * SCA[m] * SCB[n], 1/127^2, bias[n]) ),
 // in-kernel, which removes the 2 x M x N x 4-byte int32 round trip through HBM.
-#include <cstdio>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -46,27 +45,7 @@ template <bool PAIR> struct I8Cfg {
     static constexpr int kStages = kI8RingBytes / kStageBytes;  // 4 x 48 KB or 6 x 32 KB
 };
 
-// Every mbarrier wait in this kernel is bounded: a wait that has not completed after 10 s (a protocol
-// bug, or a peer CTA that died) reports itself and traps, so the failure surfaces as a CUDA error at
-// the next synchronisation instead of a hung device.  The check costs one clock read per 16K polls.
-__device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, int a, int b) {
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    while (!ptx::mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FFF) == 0) {
-            uint64_t now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) {
-                t0 = now;
-            } else if (now - t0 > 10000000000ull) {
-                if ((threadIdx.x & 31) == 0)
-                    printf("int8_gemm: barrier wait timed out (tag=%d block=%d warp=%d parity=%u it=%d tile=%d)\n", tag,
-                           (int)blockIdx.x, (int)(threadIdx.x >> 5), parity, a, b);
-                __trap();
-            }
-        }
-    }
-}
+// Every mbarrier wait in this kernel is bounded (ptx::mbar_wait_bounded: report + trap after 10 s).
 
 // EPI: 0 = int32 out, 1 = fp16 out, 2 = bf16 out (fused dequant)
 struct I8Params {
@@ -144,7 +123,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 for (int i = 0; i < p.kblocks; ++i, ++it) {
                     const int s = it % kI8Stages;
                     const uint32_t ph = (it / kI8Stages) & 1u;
-                    wait_wd(&empty[s], ph ^ 1u, 1, (int)it, pt);
+                    ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, (int)it, pt);
                     uint8_t* sa = stages + s * kI8StageBytes;
                     if (PAIR) {
                         // both CTAs' boxes complete on the LEADER's barrier: it waits once per stage
@@ -172,13 +151,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         // pair mode: only the leader issues; its instructions drive both SMs
         for (int pt = (!PAIR || rank == 0) ? cluster_id : p.pair_tiles; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
             const uint32_t acc = tcount & 1u;
-            wait_wd(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);  // epilogue has drained this accumulator
+            ptx::mbar_wait_bounded(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);  // epilogue has drained this accumulator
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kI8TileN;
             for (int i = 0; i < p.kblocks; ++i, ++it) {
                 const int s = it % kI8Stages;
                 const uint32_t ph = (it / kI8Stages) & 1u;
-                wait_wd(&full[s], ph, 3, (int)it, pt);
+                ptx::mbar_wait_bounded(&full[s], ph, 3, (int)it, pt);
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = ptx::smem_u32(stages + s * kI8StageBytes);
@@ -234,7 +213,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             }
             float sca = 0.f;
             if (EPI != 0 && m_ok) sca = __ldg(p.SCA + m);
-            wait_wd(&tmem_full[acc], (tcount >> 1) & 1u, 4, (int)tcount, pt);
+            ptx::mbar_wait_bounded(&tmem_full[acc], (tcount >> 1) & 1u, 4, (int)tcount, pt);
             ptx::tc_fence_after();
             const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * kI8TileN;
 #pragma unroll 1

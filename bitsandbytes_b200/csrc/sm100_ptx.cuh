@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace bnb200 {
 namespace ptx {
@@ -58,6 +59,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// Bounded wait: a wait that has not completed after 10 s (a protocol bug, or a peer CTA that died)
+// reports itself and traps, so the failure surfaces as a CUDA error at the next synchronisation
+// instead of a hung device.  Costs one clock read per 16K polls.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int tag, int a = 0, int b = 0) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFF) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > 10000000000ull) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("bnb200: mbarrier wait timed out (tag=%d block=%d warp=%d parity=%u a=%d b=%d)\n", tag,
+                           (int)blockIdx.x, (int)(threadIdx.x >> 5), parity, a, b);
+                __trap();
+            }
+        }
     }
 }
 

@@ -28,6 +28,10 @@ void launch_gemv4_simt(const T* A, const uint8_t* B, const float* absmax, const 
                        const float* absmax_code, const float* absmax_offset, const float* lut16, int quant_type,
                        T* out, const T* bias, int M, int N, int K, int ldc, int blocksize, cudaStream_t stream);
 template <typename T>
+bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
+                      int ldc, int blocksize, int quant_type, cudaStream_t stream);
+template <typename T>
 bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
                      int ldc, int blocksize, int quant_type, cudaStream_t stream);
@@ -116,12 +120,23 @@ bool encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int swiz
 }
 
 // ---------------------------------------------------------------- 4-bit GEMM dispatch
-// path: 0 = SIMT GEMV, 1 = tcgen05, 2 = SIMT generic (same kernel as 0, named for bookkeeping)
+// path: 0 = CUDA-core GEMV, 1 = tcgen05 GEMM, 2 = CUDA-core generic, 3 = mma.sync decode kernel (M <= 8)
 static int simt_max_m() {
     static int v = -2;
     if (v == -2) {
         const char* e = getenv("BNB_B200_SIMT_MAX_M");
         v = e ? atoi(e) : 1;  // measured on B200: the CUDA-core GEMV wins only at M == 1 (9.8 vs 14.5 us at 4096^2)
+    }
+    return v;
+}
+
+// path 3: the mma.sync decode kernel (gemv4_mma.cu), M <= 8
+static int mma_max_m() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("BNB_B200_MMA_MAX_M");
+        v = e ? atoi(e) : 8;
+        if (v > 8) v = 8;
     }
     return v;
 }
@@ -137,11 +152,12 @@ static bool tc_shape_ok(int M, int N, int K, int blocksize, int dtype) {
 
 static int choose_path(int M, int N, int K, int blocksize, int dtype) {
     if (t_forced_path >= 0) {
-        if (t_forced_path == 1 && !tc_shape_ok(M, N, K, blocksize, dtype)) return 2;
+        if ((t_forced_path == 1 || t_forced_path == 3) && !tc_shape_ok(M, N, K, blocksize, dtype)) return 2;
         return t_forced_path;
     }
     if (!tc_shape_ok(M, N, K, blocksize, dtype)) return 2;
     if (M <= simt_max_m()) return 0;
+    if (M <= mma_max_m()) return 3;
     return 1;
 }
 
@@ -155,6 +171,16 @@ static void gemm_4bit_dispatch(const T* A, const uint8_t* B, const float* absmax
         return;
     }
     const int path = choose_path(M, N, K, blocksize, dtype);
+    if (path == 3) {
+        if constexpr (!std::is_same<T, float>::value) {
+            if (launch_gemv4_mma<T>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc,
+                                    blocksize, quant_type, stream))
+                return;
+            if (launch_gemm4_tc<T>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc,
+                                   blocksize, quant_type, stream))
+                return;
+        }
+    }
     if (path == 1) {
         if constexpr (!std::is_same<T, float>::value) {
             if (launch_gemm4_tc<T>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc,

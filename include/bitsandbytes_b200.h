@@ -132,8 +132,9 @@ const char* cbnb_b200_build_info(void);
  * dtype 0 = fp32, 1 = fp16, 2 = bf16. */
 void cbnb_b200_quantize_blockwise(const float* code, const void* A, float* absmax, unsigned char* out, int blocksize, int n, int quant_type, int dtype, bnb_stream_t stream);
 
-/* Which kernel a (M, N, K, blocksize, dtype) 4-bit GEMM takes: 0 = SIMT GEMV,
- * 1 = tcgen05, 2 = generic SIMT.  For tests / bench bookkeeping. */
+/* Which kernel a (M, N, K, blocksize, dtype) 4-bit GEMM takes: 0 = CUDA-core GEMV,
+ * 1 = tcgen05 GEMM, 2 = generic CUDA-core kernel, 3 = mma.sync decode kernel (M <= 8).
+ * For tests / bench bookkeeping. */
 int cbnb_b200_gemm_4bit_path(int M, int N, int K, int blocksize, int dtype);
 /* Force a path for the next calls on this thread (-1 = automatic). */
 void cbnb_b200_gemm_4bit_force_path(int path);

@@ -114,6 +114,53 @@ def test_variants_vs_oracle(dtype, qt, nested, bias, bs):
         assert_close_to_exact(got, exact(p), dtype, K)
 
 
+# the mma.sync decode kernel (path 3): every M it serves, ragged N, K tails inside a 256-wide chunk,
+# blocksize 32 (two scales per lane) up to blocksize > chunk, both dtypes / code books, nested, bias
+@pytest.mark.parametrize("M,N,K", [(1, 128, 64), (1, 4096, 4096), (2, 130, 128), (5, 48, 320), (8, 16, 256),
+                                   (7, 40, 704), (6, 384, 512), (8, 1000, 1024), (8, 14336, 512)])
+def test_decode_kernel_vs_oracle(M, N, K):
+    p = make_problem(M, N, K, "nf4", "bf16")
+    assert nat.lib.cbnb_b200_gemm_4bit_path(M, N, K, p["bs"], 2) in (0, 3)
+    nat.lib.cbnb_b200_gemm_4bit_force_path(3)
+    try:
+        got = run(nat.lib, p)
+    finally:
+        nat.lib.cbnb_b200_gemm_4bit_force_path(-1)
+    nat.check()
+    assert_close_to_exact(got, exact(p), "bf16", K)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("qt", ["nf4", "fp4"])
+@pytest.mark.parametrize("nested,bias,bs", [(False, True, 64), (True, False, 64), (True, True, 128), (False, False, 32),
+                                            (False, True, 512)])
+def test_decode_kernel_variants_vs_oracle(dtype, qt, nested, bias, bs):
+    M, N, K = 7, 512, 768
+    p = make_problem(M, N, K, qt, dtype, bs=bs, nested=nested, bias=bias, seed=4)
+    nat.lib.cbnb_b200_gemm_4bit_force_path(3)
+    try:
+        got = run(nat.lib, p)
+    finally:
+        nat.lib.cbnb_b200_gemm_4bit_force_path(-1)
+    nat.check()
+    assert_close_to_exact(got, exact(p), dtype, K)
+
+
+def test_decode_kernel_weights_match_the_tensor_core_path():
+    """Same decoded weights, exact products: the two tensor-core paths may differ only by fp32 summation order."""
+    p = make_problem(8, 256, 2048, "nf4", "bf16", seed=9)
+    outs = []
+    for path in (3, 1):
+        nat.lib.cbnb_b200_gemm_4bit_force_path(path)
+        try:
+            outs.append(run(nat.lib, p).float())
+        finally:
+            nat.lib.cbnb_b200_gemm_4bit_force_path(-1)
+    nat.check()
+    assert torch.allclose(outs[0], outs[1], rtol=2e-2, atol=1e-3)
+    assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -6 * outs[1].abs().max().item()
+
+
 @pytest.mark.parametrize("M,N,K", [(1, 64, 96), (4, 100, 72), (7, 33, 200)])
 def test_fp32_and_odd_shapes_take_the_cuda_core_path(M, N, K):
     p = make_problem(M, N, K, "nf4", "fp32", bs=64 if (N * K) % 64 == 0 else 32)

@@ -39,10 +39,15 @@ constexpr int kI8RingBytes = 192 * 1024;
 //               weight tile, half of it fetched by its peer and multicast (48 KB into each SM).
 // Measured at 4096 x 11008 x 4096 (profiles/r01_int8_gemm_{pair,mc}.json): pair 135 us with 1.44 GB
 // crossing the L2 -> SM crossbar, multicast 140-151 us with 2.17 GB; tensor pipe 68 % active in both.
-template <bool PAIR> struct I8Cfg {
-    static constexpr int kBBytes = (PAIR ? kI8TileN / 2 : kI8TileN) * 128;
-    static constexpr int kStageBytes = kI8ABytes + kBBytes;
-    static constexpr int kStages = kI8RingBytes / kStageBytes;  // 4 x 48 KB or 6 x 32 KB
+// KSUB = 128-byte k sub-tiles per pipeline stage: with 2, the MMA thread pays one barrier wait and one
+// commit per eight tcgen05.mma instead of per four.
+template <bool PAIR, int KSUB> struct I8Cfg {
+    static constexpr int kASubBytes = kI8ABytes;                                   // 128 rows x 128 B
+    static constexpr int kBSubBytes = (PAIR ? kI8TileN / 2 : kI8TileN) * 128;
+    static constexpr int kABytes = KSUB * kASubBytes;
+    static constexpr int kBBytes = KSUB * kBSubBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = kI8RingBytes / kStageBytes;  // pair: 6 x 32 KB or 3 x 64 KB; multicast: 4 x 48 KB
 };
 
 // Every mbarrier wait in this kernel is bounded (ptx::mbar_wait_bounded: report + trap after 10 s).
@@ -58,15 +63,16 @@ struct I8Params {
     int n_tiles, m_pairs, pair_tiles;
 };
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, int KSUB>
 __global__ void __launch_bounds__(kI8Threads, 1)
     int8_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const I8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stages = smem;
-    constexpr int kI8Stages = I8Cfg<PAIR>::kStages;
-    constexpr int kI8StageBytes = I8Cfg<PAIR>::kStageBytes;
+    using Cfg = I8Cfg<PAIR, KSUB>;
+    constexpr int kI8Stages = Cfg::kStages;
+    constexpr int kI8StageBytes = Cfg::kStageBytes;
     float* s_scb = reinterpret_cast<float*>(smem + kI8Stages * kI8StageBytes);   // [2][256]
     float* s_bias = s_scb + 2 * kI8TileN;                                          // [2][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kI8Stages * kI8StageBytes + 4096);
@@ -129,16 +135,26 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                         // both CTAs' boxes complete on the LEADER's barrier: it waits once per stage
                         const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], kI8Cluster * kI8StageBytes);
-                        ptx::tma_load_2d_pair(sa, &tmap_a, lead_full, i * kI8BK, m0);
-                        ptx::tma_load_2d_pair(sa + kI8ABytes, &tmap_b, lead_full, i * kI8BK,
-                                              n0 + (int)rank * (kI8TileN / kI8Cluster));
+                        // (k columns past K are out of bounds for the tensor map: TMA zero-fills them)
+#pragma unroll
+                        for (int u = 0; u < KSUB; ++u) {
+                            const int kc = (i * KSUB + u) * kI8BK;
+                            ptx::tma_load_2d_pair(sa + u * Cfg::kASubBytes, &tmap_a, lead_full, kc, m0);
+                            ptx::tma_load_2d_pair(sa + Cfg::kABytes + u * Cfg::kBSubBytes, &tmap_b, lead_full, kc,
+                                                  n0 + (int)rank * (kI8TileN / kI8Cluster));
+                        }
                     } else {
                         ptx::mbar_arrive_expect_tx(&full[s], kI8StageBytes);
-                        ptx::tma_load_2d(sa, &tmap_a, &full[s], i * kI8BK, m0);
-                        // my half of the weight tile, to both CTAs
-                        ptx::tma_load_2d_multicast(sa + kI8ABytes + rank * (I8Cfg<PAIR>::kBBytes / kI8Cluster), &tmap_b,
-                                                   &full[s], i * kI8BK, n0 + (int)rank * (kI8TileN / kI8Cluster),
-                                                   kMask);
+#pragma unroll
+                        for (int u = 0; u < KSUB; ++u) {
+                            const int kc = (i * KSUB + u) * kI8BK;
+                            ptx::tma_load_2d(sa + u * Cfg::kASubBytes, &tmap_a, &full[s], kc, m0);
+                            // my half of the weight tile, to both CTAs
+                            ptx::tma_load_2d_multicast(sa + Cfg::kABytes + u * Cfg::kBSubBytes +
+                                                           rank * (Cfg::kBSubBytes / kI8Cluster),
+                                                       &tmap_b, &full[s], kc, n0 + (int)rank * (kI8TileN / kI8Cluster),
+                                                       kMask);
+                        }
                     }
                 }
             }
@@ -161,14 +177,18 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = ptx::smem_u32(stages + s * kI8StageBytes);
-                    const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
-                    const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + kI8ABytes);
 #pragma unroll
-                    for (int j = 0; j < kI8BK / 32; ++j) {
-                        if (PAIR)
-                            ptx::mma_i8_ss_pair(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
-                        else
-                            ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0 ? 1u : 0u);
+                    for (int u = 0; u < KSUB; ++u) {
+                        const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa + u * Cfg::kASubBytes);
+                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + Cfg::kABytes + u * Cfg::kBSubBytes);
+#pragma unroll
+                        for (int j = 0; j < kI8BK / 32; ++j) {
+                            const uint32_t accum = (i | u | j) != 0 ? 1u : 0u;
+                            if (PAIR)
+                                ptx::mma_i8_ss_pair(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, accum);
+                            else
+                                ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, accum);
+                        }
                     }
                     if (PAIR) {
                         ptx::tc_commit_pair(&empty[s], kMask);
@@ -292,11 +312,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     }
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, int KSUB>
 int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
-    constexpr size_t smem_bytes = 1024 + size_t(I8Cfg<PAIR>::kStages) * I8Cfg<PAIR>::kStageBytes + 4096 + 256;
+    using Cfg = I8Cfg<PAIR, KSUB>;
+    constexpr size_t smem_bytes = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + 4096 + 256;
     static bool attr_set = false;
-    auto kern = int8_gemm_tc_kernel<EPI, PAIR>;
+    auto kern = int8_gemm_tc_kernel<EPI, PAIR, KSUB>;
+    p.kblocks = (p.K + KSUB * kI8BK - 1) / (KSUB * kI8BK);
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("int8_gemm_tc smem attr", cudaGetLastError());
@@ -354,23 +376,33 @@ int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const
     p.N = N;
     p.K = K;
     p.ldc = ldc;
-    p.kblocks = (K + kI8BK - 1) / kI8BK;
     // BNB_B200_I8_MODE=multicast selects the cta_group::1 variant (A/B measurements); default = pair
     static const bool pair = [] {
         const char* e = getenv("BNB_B200_I8_MODE");
         return !(e != nullptr && e[0] == 'm');
     }();
+    static const int ksub = [] {
+        const char* e = getenv("BNB_B200_I8_KSUB");
+        return (e != nullptr && e[0] == '1') ? 1 : 2;
+    }();
+    if (pair && ksub == 2) {
+        switch (epi) {
+        case 0: return launch_i8<0, true, 2>(ta, tb, p, stream);
+        case 1: return launch_i8<1, true, 2>(ta, tb, p, stream);
+        default: return launch_i8<2, true, 2>(ta, tb, p, stream);
+        }
+    }
     if (pair) {
         switch (epi) {
-        case 0: return launch_i8<0, true>(ta, tb, p, stream);
-        case 1: return launch_i8<1, true>(ta, tb, p, stream);
-        default: return launch_i8<2, true>(ta, tb, p, stream);
+        case 0: return launch_i8<0, true, 1>(ta, tb, p, stream);
+        case 1: return launch_i8<1, true, 1>(ta, tb, p, stream);
+        default: return launch_i8<2, true, 1>(ta, tb, p, stream);
         }
     }
     switch (epi) {
-    case 0: return launch_i8<0, false>(ta, tb, p, stream);
-    case 1: return launch_i8<1, false>(ta, tb, p, stream);
-    default: return launch_i8<2, false>(ta, tb, p, stream);
+    case 0: return launch_i8<0, false, 1>(ta, tb, p, stream);
+    case 1: return launch_i8<1, false, 1>(ta, tb, p, stream);
+    default: return launch_i8<2, false, 1>(ta, tb, p, stream);
     }
 }
 

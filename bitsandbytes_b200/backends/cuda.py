@@ -18,6 +18,7 @@ process.
 """
 from __future__ import annotations
 
+import ctypes as ct
 from math import prod
 from typing import Optional, Sequence
 from warnings import warn
@@ -197,6 +198,34 @@ def gemm_4bit_into(A, B, shapeB, absmax, blocksize, quant_type, bias, absmax_8bi
             out.data_ptr(), bias.data_ptr() if bias is not None else None,
             M, N, K, ldc, blocksize, _QT_ID[quant_type], _DTYPE_ID[A.dtype], _stream(A))
     lib.check("gemm_4bit")
+
+
+def gemm_4bit_multi_out(A, B, shapeB, absmax, blocksize: int, quant_type: str, bias, absmax_8bit, absmax_code,
+                        absmax_offset, out_ptrs, ldc: int) -> bool:
+    """Fused GEMM + all-gather: every output element is stored to each raw device address in
+    ``out_ptrs`` (local buffer first, then the peers' -- symmetric memory / CUDA IPC mappings), row
+    stride ``ldc`` elements.  Returns False when the shape does not take the tcgen05 kernel (the caller
+    falls back to a local output + a collective)."""
+    N, K = shapeB
+    M = A.numel() // K
+    if A.dtype not in (torch.float16, torch.bfloat16):
+        return False
+    if not 1 <= len(out_ptrs) <= 8:
+        raise RuntimeError("gemm_4bit_multi_out: between 1 and 8 destinations")
+    A = A.contiguous()
+    B = B.contiguous()
+    off = absmax_offset.to(dtype=torch.float32).contiguous() if absmax_offset is not None else None
+    arr = (ct.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+    with _on_device(A):
+        rc = lib.cbnb_b200_gemm_4bit_multi_out(
+            A.data_ptr(), B.data_ptr(), absmax.data_ptr(),
+            absmax_8bit.data_ptr() if absmax_8bit is not None else None,
+            absmax_code.data_ptr() if absmax_code is not None else None,
+            off.data_ptr() if off is not None else None,
+            ct.cast(arr, ct.c_void_p), len(out_ptrs), bias.data_ptr() if bias is not None else None,
+            M, N, K, ldc, blocksize, _QT_ID[quant_type], _DTYPE_ID[A.dtype], _stream(A))
+    lib.check("gemm_4bit_multi_out")
+    return rc == 0
 
 
 @kernel("gemm_4bit")

@@ -2,9 +2,11 @@
 the Llama-3-70B FFN shape 8192 -> 28672, column-sharded across the ranks with an NCCL
 all-gather of the partial outputs (strong scaling: the layer is fixed, ranks split it).
 
-Per step every rank runs the fused kernel on its row shard of the globally quantised weight
-(written straight into its slot of the gather buffer) and one all_gather_into_tensor exchanges
-the slices.  Reported: whole-layer TFLOPS with and without the gather, max over ranks.
+Per step every rank runs the fused kernel on its row shard of the globally quantised weight.
+Three timings, max over ranks: the GEMM alone; GEMM + NCCL all_gather_into_tensor (the baseline
+exchange); and the product path -- the GEMM epilogue stores its tile into every rank's
+symmetric-memory output buffer over NVLink (parallel.fused_forward: no collective, one
+symmetric-memory barrier per step).  `value` is the product path when it is available.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ def run_sharded70b(args, rank: int, world: int, local_rank: int) -> None:
     import torch.distributed as dist
 
     from . import functional as F
-    from .parallel import ColumnParallelLinear4bit, slice_quantized_weight
+    from .parallel import ColumnParallelLinear4bit, PeerGather, fused_forward, slice_quantized_weight
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -66,16 +68,39 @@ def run_sharded70b(args, rank: int, world: int, local_rank: int) -> None:
     t0 = time.perf_counter()
     ms_gemm = timed(gemm_only)
     ms_all = timed(gemm_gather)
+    ms_fused, fused_note = None, None
+    if world > 1:
+        try:
+            peers = PeerGather(M, N_FULL, torch.bfloat16, dev)
+
+            def gemm_fused(i):
+                fused_forward(layer, xs[i % 3], peers)
+
+            # parity of the exchange before timing it: fused result == NCCL-gathered result, bit for bit
+            ref = layer(xs[0]).reshape(M, N_FULL).clone()
+            got = fused_forward(layer, xs[0], peers)
+            torch.cuda.synchronize()
+            if not torch.equal(ref, got):
+                raise RuntimeError("fused peer-store gather differs from the NCCL gather")
+            ms_fused = timed(gemm_fused)
+        except Exception as exc:  # noqa: BLE001  (no symmetric memory on this box: report and keep the NCCL number)
+            fused_note = repr(exc)[:300]
     wall = time.perf_counter() - t0
+    ms_value = ms_fused if ms_fused is not None else ms_all
     if rank == 0:
         line = {
-            "metric": "fp4_dq_column_sharded_linear_tflops", "value": flops * args.steps / (ms_all * 1e-3) / 1e12,
+            "metric": "fp4_dq_column_sharded_linear_tflops", "value": flops * args.steps / (ms_value * 1e-3) / 1e12,
             "unit": "TFLOPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "sharded70b", "N": N_FULL, "K": K_FULL, "M": M, "quant_type": "fp4",
                        "double_quant": True, "blocksize": 64, "parallelism": f"column-sharded x{world} + all-gather",
                        "rows_per_rank": shard.rows},
+            "exchange": ("GEMM epilogue peer stores into symmetric memory (no collective)" if ms_fused is not None
+                         else "NCCL all_gather_into_tensor"),
+            "fused_peer_store_tflops": None if ms_fused is None else flops * args.steps / (ms_fused * 1e-3) / 1e12,
+            "nccl_gather_tflops": flops * args.steps / (ms_all * 1e-3) / 1e12,
+            "fused_unavailable": fused_note,
             "gemm_only_tflops": flops * args.steps / (ms_gemm * 1e-3) / 1e12,
             "gemm_only_ms_per_step": ms_gemm / args.steps,
             "gather_bytes_per_rank": 2 * M * shard.rows * (world - 1),

@@ -34,7 +34,8 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
 template <typename T>
 bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
-                     int ldc, int blocksize, int quant_type, cudaStream_t stream);
+                     int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers = nullptr,
+                     int n_peers = 0);
 void launch_int8_vector_quant(const void* A, int8_t* out, float* rowStats, int* col_flags, float threshold, int rows,
                               int cols, int dtype, cudaStream_t stream);
 void launch_dequant_mm_int32_fp16(const int* A, const float* rowStats, const float* colStats, __half* out,
@@ -299,6 +300,32 @@ void cbnb_b200_gemm_4bit_strided(const void* A, const uint8_t* B, const float* a
                                           quant_type, 2, stream);
     else
         set_last_error_msg("gemm_4bit_strided: bad dtype");
+}
+
+// Fused all-gather: the tcgen05 kernel's epilogue stores every output element to outs[0..n_outs)
+// (outs[0] = the local buffer, the rest = the same location in the peer GPUs' buffers, mapped into
+// this process -- CUDA IPC / symmetric memory).  Returns 0, or 100 when the shape does not take
+// the tcgen05 path (the caller then falls back to local output + a collective).
+int cbnb_b200_gemm_4bit_multi_out(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                                  const float* absmax_code, const float* absmax_offset, void* const* outs, int n_outs,
+                                  const void* bias, int M, int N, int K, int ldc, int blocksize, int quant_type,
+                                  int dtype, cudaStream_t stream) {
+    if (n_outs < 1 || n_outs > 8 || outs == nullptr) {
+        set_last_error_msg("gemm_4bit_multi_out: 1 <= n_outs <= 8");
+        return 1;
+    }
+    if (M <= 0 || N <= 0) return 0;
+    if (!tc_shape_ok(M, N, K, blocksize, dtype)) return 100;
+    bool ok = false;
+    if (dtype == 1)
+        ok = launch_gemm4_tc<__half>((const __half*)A, B, absmax, absmax_8bit, absmax_code, absmax_offset,
+                                     (__half*)outs[0], (const __half*)bias, M, N, K, ldc, blocksize, quant_type, stream,
+                                     outs + 1, n_outs - 1);
+    else if (dtype == 2)
+        ok = launch_gemm4_tc<__nv_bfloat16>((const __nv_bfloat16*)A, B, absmax, absmax_8bit, absmax_code,
+                                            absmax_offset, (__nv_bfloat16*)outs[0], (const __nv_bfloat16*)bias, M, N, K,
+                                            ldc, blocksize, quant_type, stream, outs + 1, n_outs - 1);
+    return ok ? 0 : 100;
 }
 
 int cbnb_b200_gemm_4bit_path(int M, int N, int K, int blocksize, int dtype) {

@@ -58,6 +58,8 @@ struct Gemm4Params {
     const float* absmax_offset;  // scalar
     const void* bias;            // T[N] or NULL
     void* out;                   // T[M, ldc]
+    void* peer_out[7];           // further copies of the output tile (peer GPUs' gather buffers, same ldc): the
+    int n_peers;                 //   epilogue stores every element to all of them (fused all-gather)
     float* ws_partial;           // split-K partials [tiles][splits][128][MT]
     int* ws_counter;             // one per output tile, zero on entry, reset on exit
     int M, N, K, ldc;
@@ -368,8 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int t = 0; t < kChunk; ++t) {
                     const int m = m0 + col0 + c + t;
-                    if (n_ok && m < p.M && !(p.debug & 16))
-                        outp[(long long)m * p.ldc + n] = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
+                    if (n_ok && m < p.M && !(p.debug & 16)) {
+                        const T val = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
+                        const long long idx = (long long)m * p.ldc + n;
+                        outp[idx] = val;
+                        for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<T*>(p.peer_out[r])[idx] = val;
+                    }
                 }
             }
         } else {
@@ -418,7 +424,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                     float acc = 0.f;
                     for (int sp = 0; sp < splits; ++sp)
                         acc += __ldcg(ws_tile + ((long long)sp * MT + c) * kTileN + rn);
-                    if (nn < p.N) outp[(long long)m * p.ldc + nn] = DT<T>::from_f32(acc + bias_r);
+                    if (nn < p.N) {
+                        const T val = DT<T>::from_f32(acc + bias_r);
+                        const long long idx = (long long)m * p.ldc + nn;
+                        outp[idx] = val;
+                        for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<T*>(p.peer_out[r])[idx] = val;
+                    }
                 }
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -660,10 +671,12 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
 } // namespace
 
 // Returns true if the tensor-core path handled the call.
+// `peers` / `n_peers`: up to 7 additional output bases (same ldc) that receive a copy of every element.
 template <typename T>
 bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
-                     int ldc, int blocksize, int quant_type, cudaStream_t stream) {
+                     int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers, int n_peers) {
+    if (n_peers < 0 || n_peers > 7) return false;
     if (M <= 0 || N <= 0) return true;
     if (K < 64 || (K % 64) != 0) return false;
     if (blocksize < 32 || (blocksize & (blocksize - 1)) != 0) return false;
@@ -684,6 +697,8 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     p.absmax_offset = absmax_offset;
     p.bias = bias;
     p.out = out;
+    p.n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) p.peer_out[r] = peers[r];
     p.M = M;
     p.N = N;
     p.K = K;
@@ -733,9 +748,9 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
 
 template bool launch_gemm4_tc<__nv_bfloat16>(const __nv_bfloat16*, const uint8_t*, const float*, const uint8_t*,
                                              const float*, const float*, __nv_bfloat16*, const __nv_bfloat16*, int,
-                                             int, int, int, int, int, cudaStream_t);
+                                             int, int, int, int, int, cudaStream_t, void* const*, int);
 template bool launch_gemm4_tc<__half>(const __half*, const uint8_t*, const float*, const uint8_t*, const float*,
                                       const float*, __half*, const __half*, int, int, int, int, int, int,
-                                      cudaStream_t);
+                                      cudaStream_t, void* const*, int);
 
 } // namespace bnb200

@@ -20,6 +20,14 @@ all-gather.  The gather is along the inner dimension of a row-major matrix, whic
 ``all_gather_into_tensor`` cannot write in place, so the exchange runs on a ``[world, M,
 N/world]`` staging buffer; ``gather_output=False`` hands back the local slice instead (what
 a following row-parallel layer wants).
+
+Fused exchange (``PeerGather`` + ``forward_fused``): the output lives in symmetric memory
+(``torch.distributed._symmetric_memory``: one ``[M, N]`` buffer per rank, every rank holds the
+peers' mappings) and the GEMM epilogue stores each output element into ITS columns of EVERY rank's
+buffer -- the all-gather rides on the kernel's own stores over NVLink / NVSwitch, tile by tile,
+there is no separate collective and no permute; one symmetric-memory barrier per step publishes
+the result.  Buffers alternate between two slots so that a rank may start step i + 1 while a peer
+still reads step i.
 """
 from __future__ import annotations
 
@@ -30,7 +38,7 @@ import torch
 import torch.distributed as dist
 
 from . import functional as F
-from .backends.cuda import gemm_4bit_into
+from .backends.cuda import gemm_4bit_into, gemm_4bit_multi_out
 
 
 @dataclass
@@ -123,6 +131,52 @@ class ColumnParallelLinear4bit(torch.nn.Module):
         dist.all_gather_into_tensor(self._stage.view(-1), self._stage[rank].reshape(-1), group=self.group)
         # [world, M, rows] -> [M, world*rows]
         return self._stage.permute(1, 0, 2).reshape(*lead, world * s.rows)
+
+
+class PeerGather:
+    """Two symmetric-memory ``[M, N]`` output slots shared by the ranks of ``group``."""
+
+    def __init__(self, M: int, N: int, dtype: torch.dtype, device, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.M, self.N, self.dtype = M, N, dtype
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty((M, N), dtype=dtype, device=device)
+            self.handles.append(symm_mem.rendezvous(t, group))
+            self.bufs.append(t)
+        self.world = self.handles[0].world_size
+        self.rank = self.handles[0].rank
+        self.step = 0
+
+    def slot(self):
+        """(local tensor, [base address of that slot on rank r for every r], handle) of the next step."""
+        i = self.step & 1
+        self.step += 1
+        return self.bufs[i], [int(p) for p in self.handles[i].buffer_ptrs], self.handles[i]
+
+
+def fused_forward(layer: "ColumnParallelLinear4bit", x: torch.Tensor, peers: PeerGather) -> torch.Tensor:
+    """``layer(x)`` with the all-gather fused into the GEMM epilogue; returns this rank's [M, N] slot."""
+    s = layer.shard
+    M = x.numel() // s.K
+    if M != peers.M or layer.out_features != peers.N or x.dtype != peers.dtype:
+        raise ValueError("PeerGather was built for a different output shape / dtype")
+    local, bases, handle = peers.slot()
+    col_bytes = s.row0 * local.element_size()
+    # own buffer first, then the peers
+    order = [peers.rank] + [r for r in range(peers.world) if r != peers.rank]
+    ptrs = [bases[r] + col_bytes for r in order]
+    ok = gemm_4bit_multi_out(x, s.packed, (s.rows, s.K), s.absmax, s.blocksize, s.quant_type, layer.bias_shard,
+                             s.absmax_8bit, s.absmax_code, s.absmax_offset, ptrs, peers.N)
+    if not ok:  # shape outside the tensor-core kernel: local slice + NCCL all-gather into the same slot
+        stage = torch.empty((peers.world, M, s.rows), device=x.device, dtype=x.dtype)
+        layer.local_forward(x, stage[peers.rank], s.rows)
+        dist.all_gather_into_tensor(stage.view(-1), stage[peers.rank].reshape(-1), group=layer.group)
+        local.copy_(stage.permute(1, 0, 2).reshape(M, peers.N))
+    handle.barrier(channel=0)  # every rank's stores have landed everywhere
+    return local
 
 
 def reassemble_shards(shards: list[Shard4bit]) -> tuple[torch.Tensor, torch.Tensor]:

@@ -132,6 +132,13 @@ const char* cbnb_b200_build_info(void);
  * dtype 0 = fp32, 1 = fp16, 2 = bf16. */
 void cbnb_b200_quantize_blockwise(const float* code, const void* A, float* absmax, unsigned char* out, int blocksize, int n, int quant_type, int dtype, bnb_stream_t stream);
 
+/* Fused all-gather for a column-sharded layer (no reference counterpart: the reference is single-device).
+ * The tcgen05 kernel's epilogue stores every output element to outs[0..n_outs): outs[0] is the local
+ * [M, ldc] buffer, the others the same location in the peer GPUs' buffers mapped into this process
+ * (CUDA IPC / symmetric memory), so the exchange rides on the GEMM's own stores over NVLink.
+ * `outs` is a HOST array.  Returns 0, or 100 if the shape does not take the tcgen05 path. */
+int cbnb_b200_gemm_4bit_multi_out(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset, void* const* outs, int n_outs, const void* bias, int M, int N, int K, int ldc, int blocksize, int quant_type, int dtype, bnb_stream_t stream);
+
 /* Which kernel a (M, N, K, blocksize, dtype) 4-bit GEMM takes: 0 = CUDA-core GEMV,
  * 1 = tcgen05 GEMM, 2 = generic CUDA-core kernel, 3 = mma.sync decode kernel (M <= 8).
  * For tests / bench bookkeeping. */

@@ -179,6 +179,48 @@ def test_split_k_is_deterministic_and_workspace_self_resets():
     assert_close_to_exact(a, exact(p), "bf16", 4096)
 
 
+def test_multi_destination_epilogue_writes_every_buffer():
+    """The fused all-gather epilogue on one GPU: three 'peer' buffers on the same device must all receive
+    this shard's columns, bit-identical to the plain call, and nothing else may be touched."""
+    import ctypes as ct
+
+    M, N, K, NF = 300, 256, 512, 1024  # shard of 256 features at column 384 of a 1024-wide output
+    p = make_problem(M, N, K, "nf4", "bf16", bias=True, seed=11)
+    want = run(nat.lib, p)
+    bufs = [torch.full((M, NF), -7.0, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    col0 = 384
+    ptrs = (ct.c_void_p * 3)(*[b.data_ptr() + col0 * 2 for b in bufs])
+    rc = nat.lib.cbnb_b200_gemm_4bit_multi_out(
+        nat.ptr(p["x"]), nat.ptr(p["packed"]), nat.ptr(p["absmax"]), None, None, None, ct.cast(ptrs, ct.c_void_p), 3,
+        nat.ptr(p["bias"]), M, N, K, NF, p["bs"], nat.QT_ID["nf4"], 2, nat.stream())
+    torch.cuda.synchronize()
+    nat.check()
+    assert rc == 0
+    for b in bufs:
+        assert torch.equal(b[:, col0:col0 + N], want)
+        assert (b[:, :col0] == -7.0).all() and (b[:, col0 + N:] == -7.0).all()
+    # split-K shapes take the cooperative reduction: same contract
+    M2 = 24
+    p2 = make_problem(M2, N, 4096, "nf4", "bf16", seed=12)
+    nat.lib.cbnb_b200_gemm_4bit_force_path(1)
+    try:
+        want2 = run(nat.lib, p2)
+    finally:
+        nat.lib.cbnb_b200_gemm_4bit_force_path(-1)
+    bufs2 = [torch.zeros((M2, N), dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    ptrs2 = (ct.c_void_p * 2)(*[b.data_ptr() for b in bufs2])
+    rc = nat.lib.cbnb_b200_gemm_4bit_multi_out(
+        nat.ptr(p2["x"]), nat.ptr(p2["packed"]), nat.ptr(p2["absmax"]), None, None, None, ct.cast(ptrs2, ct.c_void_p),
+        2, None, M2, N, 4096, N, p2["bs"], nat.QT_ID["nf4"], 2, nat.stream())
+    torch.cuda.synchronize()
+    nat.check()
+    assert rc == 0
+    assert torch.equal(bufs2[0], want2) and torch.equal(bufs2[1], want2)
+    # fp32 activations do not take the tensor-core kernel: the entry point says so instead of computing
+    assert nat.lib.cbnb_b200_gemm_4bit_multi_out(None, None, None, None, None, None, ct.cast(ptrs2, ct.c_void_p), 2,
+                                                 None, M2, N, 4096, N, 64, nat.QT_ID["nf4"], 0, nat.stream()) == 100
+
+
 def test_strided_output_for_sharded_linear():
     p = make_problem(32, 256, 256, "nf4", "bf16", seed=9)
     full = torch.zeros(32, 1024, device="cuda", dtype=torch.bfloat16)

@@ -57,6 +57,36 @@ def test_reference_abi_names_present():
     assert not [n for n in names if not hasattr(dll, n)]
 
 
+def test_entry_points_validate_arguments_before_touching_the_device():
+    """Argument errors are reported through the error flag without a CUDA call (so this runs on a CPU box)."""
+    from bitsandbytes_b200 import cextension
+
+    lib = cextension.lib
+    rc = lib.cbnb_b200_gemm_4bit_multi_out(None, None, None, None, None, None, None, 0, None, 16, 128, 64, 128, 64, 2, 2,
+                                           None)
+    assert rc == 1
+    with pytest.raises(RuntimeError, match="n_outs"):
+        lib.check("gemm_4bit_multi_out")
+    # nine destinations is one too many (the kernel carries the local buffer + 7 peers)
+    arr = (ct.c_void_p * 9)(*([0] * 9))
+    rc = lib.cbnb_b200_gemm_4bit_multi_out(None, None, None, None, None, None, ct.cast(arr, ct.c_void_p), 9, None, 16,
+                                           128, 64, 128, 64, 2, 2, None)
+    assert rc == 1
+    with pytest.raises(RuntimeError):
+        lib.check("gemm_4bit_multi_out")
+    # an empty problem is a no-op, and which kernel a shape would take is a pure function of the shape
+    assert lib.cbnb_b200_gemm_4bit_multi_out(None, None, None, None, None, None, ct.cast(arr, ct.c_void_p), 2, None, 0,
+                                             128, 64, 128, 64, 2, 2, None) == 0
+    path = lib.cbnb_b200_gemm_4bit_path
+    assert path(1, 4096, 4096, 64, 2) == 0      # CUDA-core GEMV
+    assert path(4, 4096, 4096, 64, 2) == 3      # mma.sync decode kernel
+    assert path(8, 4096, 4096, 64, 1) == 3
+    assert path(9, 4096, 4096, 64, 2) == 1      # tcgen05
+    assert path(4096, 4096, 4096, 64, 2) == 1
+    assert path(4, 4096, 4096, 64, 0) == 2      # fp32 activations: generic CUDA-core kernel
+    assert path(4, 4096, 4000, 64, 2) == 2      # K % 64 != 0
+
+
 def test_missing_library_fails_loudly(tmp_path):
     code = ("import os; os.environ['BNB_B200_LIBRARY']=r'%s/nope.so'\n"
             "import bitsandbytes_b200.cextension as c\n"

@@ -38,6 +38,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 namespace bnb200 {
@@ -473,10 +474,12 @@ struct WsEntry {
     bool used;
 };
 WsEntry g_ws[kMaxWs];
+std::mutex g_ws_mu;  // the registry is shared by every host thread that launches GEMMs
 
 // Split-K scratch, one per (device, stream) so that launches on different streams never
 // share partials or counters.  Grown with plain cudaMalloc on first use / growth only.
 Workspace* get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_counters) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     WsEntry* e = nullptr;

@@ -458,6 +458,240 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// EXPERIMENTAL (BNB_B200_PERSISTENT=1; written at the end of round 1, compiled, not yet run on a
+// GPU).  Same tile, same stage pipeline, same numerics as gemm4_tc_kernel for CL = 1 and no split-K,
+// but one CTA per SM walks the tiles w = blockIdx.x, blockIdx.x + gridDim.x, ...:
+//   * TMEM allocation, barrier set-up and descriptor prefetch happen once per CTA, not per tile;
+//   * the stage ring runs THROUGH tile boundaries (global stage counter): while the 16 decode warps
+//     drain the accumulator of tile t, the TMA producer already fills the ring for tile t+1;
+//   * the accumulator is handed back to the MMA thread as soon as it sits in registers
+//     (tcgen05.ld + wait::ld, then one arrive per warp on acc_empty) -- the conversion and the global
+//     stores of tile t overlap the first stages of tile t+1.
+// Every mbarrier wait is bounded (report + trap after 10 s).
+template <typename T, int QT, int MT>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm4_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                               const Gemm4Params p) {
+    using Cfg = StageCfg<MT>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kXSubBytes = Cfg::kXSubBytes;
+    constexpr int kXStageBytes = Cfg::kXStageBytes;
+    constexpr int kWStageBytes = Cfg::kWStageBytes;
+    constexpr uint32_t kTmemCols = Cfg::kTmemCols;
+    constexpr uint32_t kWCol0 = Cfg::kWCol0;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sx = smem;
+    uint8_t* sw = smem + kStages * kXStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full = bars;                     // [kStages] TMA (1 arrive + X bytes) + 8 decode warps -> MMA
+    uint64_t* empty = bars + kStages;          // [kStages] MMA -> TMA producer + decode warps
+    uint64_t* w_full = bars + 2 * kStages;     // [kStages] TMA (1 arrive + code bytes) -> decode warps
+    uint64_t* acc_full = bars + 3 * kStages;   // MMA -> epilogue            (one phase per tile)
+    uint64_t* acc_empty = acc_full + 1;        // 16 epilogue warps -> MMA   (one phase per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nst = p.kblocks_total;  // stages per tile (no split-K in this variant)
+    const int kb64_total = p.K / 64;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(&full[s], 1 + kDecodeWarps / 2);
+            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init(&w_full[s], 1);
+        }
+        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init(acc_empty, kDecodeWarps);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<kTmemCols>(tmem_slot);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;  // global stage counter
+            for (int w = blockIdx.x; w < p.tiles_total; w += gridDim.x) {
+                const int n0 = (w % p.n_tiles) * kTileN;
+                const int m0 = (w / p.n_tiles) * MT;
+                for (int i = 0; i < nst; ++i, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 11, (int)it, w);
+                    const int k0 = i * kBK;
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kWStageBytes);
+                    ptx::tma_load_2d(sw + s * kWStageBytes, &tmap_w, &w_full[s], k0 / 2, n0);
+                    ptx::mbar_arrive_expect_tx(&full[s], kXStageBytes);
+                    uint8_t* dst = sx + s * kXStageBytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        ptx::tma_load_2d(dst + h * kXSubBytes, &tmap_x, &full[s], k0 + 64 * h, m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        constexpr uint32_t idesc = ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/128, /*N=*/MT);
+        uint32_t it = 0, tc = 0;
+        for (int w = blockIdx.x; w < p.tiles_total; w += gridDim.x, ++tc) {
+            // the epilogue warps have the previous tile's accumulator in registers
+            ptx::mbar_wait_bounded(acc_empty, (tc & 1u) ^ 1u, 12, (int)tc, w);
+            ptx::tc_fence_after();
+            for (int i = 0; i < nst; ++i, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1u;
+                ptx::mbar_wait_bounded(&full[s], ph, 13, (int)it, w);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
+                    const uint64_t bdesc0 = ptx::make_sw128_kmajor_desc(xs);
+                    const uint64_t bdesc1 = ptx::make_sw128_kmajor_desc(xs + kXSubBytes);
+                    const uint32_t a_tmem = tmem_base + kWCol0 + s * 64;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3), idesc,
+                                        (i | j) != 0 ? 1u : 0u);
+                    ptx::tc_commit(&empty[s]);
+                    if (i == nst - 1) ptx::tc_commit(acc_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================== decode / epilogue warps
+        const int dw = warp - 2;
+        const int quarter = warp & 3;
+        const int grp = dw >> 3;
+        const int half = (dw >> 2) & 1;
+        const int khalf = dw >> 2;
+        const int row = quarter * 32 + lane;
+        ScaleSrc sc{p.absmax, p.absmax_8bit, p.absmax_code, p.absmax_offset ? __ldg(p.absmax_offset) : 0.0f};
+        const bool two_scales = p.log2_bs == 5;
+        const uint32_t sw_row = (uint32_t)row * 64u;
+        const uint32_t sw_c0 = (uint32_t)(((2 * half) ^ ((row >> 1) & 3)) * 16);
+        const uint32_t sw_c1 = (uint32_t)(((2 * half + 1) ^ ((row >> 1) & 3)) * 16);
+        constexpr int kColsPerWarp = MT / 4;  // 64 at MT = 256
+        static_assert(kColsPerWarp % 32 == 0, "the persistent variant serves the large-M tiles");
+        const int col0 = khalf * kColsPerWarp;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+        T* outp = reinterpret_cast<T*>(p.out);
+        const int cnt = (nst - grp + 1) >> 1;  // stages of a tile this group decodes (those with i % 2 == grp)
+
+        uint32_t it0 = 0, tc = 0;  // global index of the tile's first stage; tiles done
+        for (int w = blockIdx.x; w < p.tiles_total; w += gridDim.x, it0 += (uint32_t)nst, ++tc) {
+            const int n0 = (w % p.n_tiles) * kTileN;
+            const int m0 = (w / p.n_tiles) * MT;
+            const int n = n0 + row;
+            const bool n_ok = n < p.N;
+            const long long e_row = (long long)(n_ok ? n : 0) * p.K;
+
+            float wsc[kScaleDepth][2];
+            auto fetch = [&](int j, int t) {
+                wsc[j][0] = wsc[j][1] = 0.f;
+                const int stage_idx = 2 * t + grp;
+                const int kb = 2 * stage_idx + half;
+                if (stage_idx < nst && n_ok && kb < kb64_total) {
+                    const long long e = e_row + (long long)kb * 64;
+                    wsc[j][0] = sc.load(e >> p.log2_bs);
+                    if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < kScaleDepth; ++j) fetch(j, j);
+
+            for (int t0 = 0; t0 < cnt; t0 += kScaleDepth) {
+#pragma unroll
+                for (int j = 0; j < kScaleDepth; ++j) {
+                    const int t = t0 + j;
+                    if (t < cnt) {
+                        const int i = 2 * t + grp;          // stage inside the tile
+                        const uint32_t gi = it0 + (uint32_t)i;  // global stage: ring slot and phase
+                        const int s = gi % kStages;
+                        const uint32_t ph = (gi / kStages) & 1u;
+                        const float sc0 = wsc[j][0], sc1 = wsc[j][1];
+                        fetch(j, t + kScaleDepth);
+
+                        ptx::mbar_wait_bounded(&w_full[s], ph, 14, (int)gi, w);
+                        const uint8_t* wt = sw + s * kWStageBytes + sw_row;
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(wt + sw_c0);
+                        const uint4 q1 = *reinterpret_cast<const uint4*>(wt + sw_c1);
+                        uint32_t r[32];
+                        DecodeTable tab;
+                        build_table<T, QT>(sc0, tab);
+                        decode_word(q0.x, tab, r + 0);
+                        decode_word(q0.y, tab, r + 4);
+                        decode_word(q0.z, tab, r + 8);
+                        decode_word(q0.w, tab, r + 12);
+                        if (two_scales) build_table<T, QT>(sc1, tab);
+                        decode_word(q1.x, tab, r + 16);
+                        decode_word(q1.y, tab, r + 20);
+                        decode_word(q1.z, tab, r + 24);
+                        decode_word(q1.w, tab, r + 28);
+
+                        ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 15, (int)gi, w);
+                        ptx::tc_fence_after();
+                        const uint32_t taddr =
+                            tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 64 + half * 32;
+                        ptx::tmem_st_x32(taddr, r);
+                        ptx::tmem_wait_st();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&full[s]);
+                    }
+                }
+            }
+
+            // ---------------- epilogue of this tile: accumulator -> registers, hand TMEM back, then store
+            ptx::mbar_wait_bounded(acc_full, tc & 1u, 16, (int)tc, w);
+            ptx::tc_fence_after();
+            uint32_t v[kColsPerWarp];
+#pragma unroll
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                uint32_t v32[32];
+                ptx::tmem_ld_x32(lane_addr + col0 + c, v32);
+#pragma unroll
+                for (int z = 0; z < 32; ++z) v[c + z] = v32[z];
+            }
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_empty);  // the MMA thread may overwrite the accumulator now
+
+            float bias_v = 0.f;
+            if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
+#pragma unroll
+            for (int c = 0; c < kColsPerWarp; ++c) {
+                const int m = m0 + col0 + c;
+                if (n_ok && m < p.M) {
+                    const T val = DT<T>::from_f32(__uint_as_float(v[c]) + bias_v);
+                    const long long idx = (long long)m * p.ldc + n;
+                    outp[idx] = val;
+                    for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 struct Workspace {
     void* ptr = nullptr;
@@ -541,6 +775,15 @@ int tail_split_enabled() {
     return v;
 }
 
+int persistent_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BNB_B200_PERSISTENT");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;  // experimental, not yet measured: off
+    }
+    return v;
+}
+
 int cluster_override() {
     static int v = -2;
     if (v == -2) {
@@ -606,6 +849,33 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     }
     const int sms = wave_ctas;
     const int tiles = n_tiles * m_tiles;
+
+    // Experimental persistent variant (see gemm4_tc_persistent_kernel): more tiles than SMs, no clusters.
+    if constexpr (CL == 1 && MT >= 128) {
+        if (persistent_enabled() && tiles > sms) {
+            static bool pattr_set = false;
+            auto pkern = gemm4_tc_persistent_kernel<T, QT, MT>;
+            if (!pattr_set) {
+                if (cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) !=
+                    cudaSuccess) {
+                    set_last_error("gemm4_tc persistent smem attr", cudaGetLastError());
+                    return false;
+                }
+                pattr_set = true;
+            }
+            p.splits = 1;
+            p.splits_tail = 1;
+            p.tiles_main = tiles;
+            p.n_tiles = n_tiles;
+            p.tiles_total = tiles;
+            p.kblocks_per_split = p.kblocks_total;
+            p.ws_partial = nullptr;
+            p.ws_counter = nullptr;
+            pkern<<<sms, kThreads, smem_bytes, stream>>>(tmap, tmap_w, p);
+            BNB200_CHECK_LAUNCH("gemm4_tc_persistent");
+            return true;
+        }
+    }
     const int max_by_k = p.kblocks_total / 2 > 0 ? p.kblocks_total / 2 : 1;  // >= two 128-wide stages per split
     auto clamp_splits = [&](int v) {
         if (v > max_by_k) v = max_by_k;

@@ -20,7 +20,8 @@ One JSON line on rank 0:
 
 Multi-GPU: the default workload shards by tokens (independent units, no data-path collective):
 every rank runs the same layer on its own 4096-token batch -> "scaling": "weak".
-``--workload sharded70b`` measures the column-sharded FP4+double-quant 8192 -> 28672 layer with
+``--workload blockwise_c1`` / ``int8_c3`` cover BASELINE configs[0] (on the GPU) and configs[2]
+(bitsandbytes_b200/bench_paths.py).  ``--workload sharded70b`` measures the column-sharded FP4+double-quant 8192 -> 28672 layer with
 an NCCL all-gather of the partial outputs (BASELINE.json configs[3]; strong scaling).
 """
 import argparse
@@ -190,6 +191,11 @@ def main():
         from bitsandbytes_b200.bench_sharded import run_sharded70b
 
         return run_sharded70b(args, rank, world, local_rank)
+    if args.workload in ("blockwise_c1", "int8_c3"):
+        from bitsandbytes_b200 import bench_paths
+
+        fn = bench_paths.run_blockwise_c1 if args.workload == "blockwise_c1" else bench_paths.run_int8_c3
+        return fn(args, rank, world, local_rank)
     if args.workload == "llama8b":
         from bitsandbytes_b200.bench_e2e import run_llama8b
 

@@ -170,6 +170,45 @@ def cpu_reference(N, K, M_total, qt, packed_u8, absmax_f32, x_bf16_cpu, budget_s
                     "ms_per_sample": med * 1e3}, med, m
 
 
+def cpu_blockwise_sample(n_total, code_np):
+    """cpu_baseline of --workload blockwise_c1: the oracle port (one host thread) dequantising a bounded
+    sample of the tensor, blocksize 4096."""
+    import numpy as np
+
+    import oracle
+
+    m = 1 << 20
+    a = np.random.default_rng(0).standard_normal(m).astype(np.float32)
+    codes, absmax = oracle.quantize_blockwise(a, 4096, None, code_np)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 5.0 or reps < 3:
+        oracle.dequantize_blockwise(codes, absmax, 4096, m, None, code_np, "fp32")
+        reps += 1
+    sec = (time.perf_counter() - t0) / reps
+    return {"value": (4 * m + m + 4 * m // 4096) / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"dequantize_blockwise of {m} of {n_total} elements, blocksize 4096, mean of {reps}"}
+
+
+def cpu_int8_sample(x_fp16_cpu, cb_np, scb_np, M, N, K):
+    """cpu_baseline of --workload int8_c3: the oracle port (one host thread) on 16 token rows: row
+    quantisation (threshold 6.0) + int8 GEMM + dequantisation."""
+    import numpy as np
+    import torch
+
+    import oracle
+
+    rows = 16
+    a_bits = x_fp16_cpu[:rows].contiguous().view(torch.int16).numpy().view(np.uint16).reshape(rows, K)
+    t0 = time.perf_counter()
+    q, stats = oracle.int8_vector_quant(a_bits, 6.0)
+    acc = oracle.int8_gemm(q, cb_np)
+    oracle.int8_mm_dequant(acc, stats, scb_np)
+    sec = time.perf_counter() - t0
+    return {"value": 2.0 * rows * N * K / sec / 1e12, "unit": "TOPS", "cores": 1, "kind": "port",
+            "sample": f"{rows} of {M} token rows: row quantise + int8 GEMM + dequantise (outlier addmm not included)"}
+
+
 # ------------------------------------------------------------------------------------------ main
 def _protect_stdout():
     """Native libraries (NCCL's version banner, cuBLAS warnings) write to file descriptor 1; the
@@ -194,8 +233,10 @@ def main():
     if args.workload in ("blockwise_c1", "int8_c3"):
         from bitsandbytes_b200 import bench_paths
 
-        fn = bench_paths.run_blockwise_c1 if args.workload == "blockwise_c1" else bench_paths.run_int8_c3
-        return fn(args, rank, world, local_rank)
+        if args.workload == "blockwise_c1":
+            return bench_paths.run_blockwise_c1(args, rank, world, local_rank,
+                                                None if args.no_cpu_baseline else cpu_blockwise_sample)
+        return bench_paths.run_int8_c3(args, rank, world, local_rank, None if args.no_cpu_baseline else cpu_int8_sample)
     if args.workload == "llama8b":
         from bitsandbytes_b200.bench_e2e import run_llama8b
 

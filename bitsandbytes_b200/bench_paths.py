@@ -7,14 +7,13 @@
     Llama-3-8B FFN shape 4096 -> 11008, 4096 tokens, fp16, with the reference benchmark's five
     outlier columns (reference benchmarking/matmul_benchmark.py:47-48), through ``module.forward``.
 
-Both run on rank 0 of one GPU (they do not shard), time with CUDA events over rotating buffer sets
-larger than L2, and put the oracle port, timed on a bounded sample on one host thread, next to the
-number as ``cpu_baseline``.
+Both run on rank 0 of one GPU (they do not shard) and time with CUDA events over rotating buffer sets
+larger than L2.  ``cpu_baseline`` is a callback supplied by bench.py (the oracle port on a bounded
+sample): this package never imports ``oracle/``.
 """
 from __future__ import annotations
 
 import json
-import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -45,8 +44,7 @@ def _time_us(fn, steps, warmup):
     return e0.elapsed_time(e1) * 1e3 / steps
 
 
-def run_blockwise_c1(args, rank: int, world: int, local_rank: int) -> None:
-    import numpy as np
+def run_blockwise_c1(args, rank: int, world: int, local_rank: int, cpu_baseline=None) -> None:
     import torch
 
     from . import functional as F
@@ -82,22 +80,8 @@ def run_blockwise_c1(args, rank: int, world: int, local_rank: int) -> None:
             results[f"{name}_bs{bs}"] = {"us": us, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak,
                                          "algorithmic_bytes": algo_bytes}
 
-    # CPU baseline: the oracle port (one host thread) on a bounded sample, same op as the headline
-    cpu = None
-    if not getattr(args, "no_cpu_baseline", False):
-        import oracle
-
-        m = 1 << 20
-        a = np.random.default_rng(0).standard_normal(m).astype(np.float32)
-        codes, absmax = oracle.quantize_blockwise(a, 4096, None, code.cpu().numpy())
-        t0 = time.perf_counter()
-        reps = 0
-        while time.perf_counter() - t0 < 5.0 or reps < 3:
-            oracle.dequantize_blockwise(codes, absmax, 4096, m, None, code.cpu().numpy(), "fp32")
-            reps += 1
-        sec = (time.perf_counter() - t0) / reps
-        cpu = {"value": (4 * m + m + 4 * m // 4096) / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-               "sample": f"dequantize_blockwise of {m} of {n} elements, blocksize 4096, mean of {reps}"}
+    # CPU baseline (supplied by bench.py: the package itself never touches oracle/)
+    cpu = cpu_baseline(n, code.cpu().numpy()) if cpu_baseline is not None else None
 
     head = results["dequantize_bs4096"]
     line = {
@@ -116,8 +100,7 @@ def run_blockwise_c1(args, rank: int, world: int, local_rank: int) -> None:
     print(json.dumps(line), flush=True)
 
 
-def run_int8_c3(args, rank: int, world: int, local_rank: int) -> None:
-    import numpy as np
+def run_int8_c3(args, rank: int, world: int, local_rank: int, cpu_baseline=None) -> None:
     import torch
 
     import bitsandbytes_b200 as bnb
@@ -150,22 +133,10 @@ def run_int8_c3(args, rank: int, world: int, local_rank: int) -> None:
     peak_tops = 4500.0  # nominal dense int8 (B200_PROFILING.md); no measured int8 figure in MEASURED_PEAKS.json
 
     cpu = None
-    if not getattr(args, "no_cpu_baseline", False):
-        import oracle
-
-        rows = 16  # bounded sample: the scalar port does 16 x 11008 x 4096 MACs in a few seconds
-        a_bits = xs[0][:rows].cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    if cpu_baseline is not None:
         CB = layer.state.CB if layer.state.CB is not None else layer.weight.CB
         SCB = layer.state.SCB if layer.state.SCB is not None else layer.weight.SCB
-        cb = CB.cpu().numpy()
-        scb = SCB.float().cpu().numpy()
-        t0 = time.perf_counter()
-        q, stats = oracle.int8_vector_quant(a_bits.reshape(rows, K), 6.0)
-        acc = oracle.int8_gemm(q, cb)
-        oracle.int8_mm_dequant(acc, stats, scb)
-        sec = time.perf_counter() - t0
-        cpu = {"value": 2.0 * rows * N * K / sec / 1e12, "unit": "TOPS", "cores": 1, "kind": "port",
-               "sample": f"{rows} of {M} token rows: row quantise + int8 GEMM + dequantise (outlier addmm not included)"}
+        cpu = cpu_baseline(xs[0].cpu(), CB.cpu().numpy(), SCB.float().cpu().numpy(), M, N, K)
 
     line = {
         "metric": "linear8bitlt_forward_tops", "value": ops / us / 1e6, "unit": "TOPS", "n_gpus": 1, "steps": steps,

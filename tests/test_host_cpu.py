@@ -470,3 +470,90 @@ def test_column_parallel_linear_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o[-3000:]
+
+
+# ----------------------------------------------------------------------------------------------
+# Checkpoints written by the REFERENCE load into our modules and serialise back to the same bytes
+# (fixtures: tests/golden/make_golden_state_dicts.py, generated by importing the reference here)
+# ----------------------------------------------------------------------------------------------
+_TORCH_DT = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16, "torch.float16": torch.float16,
+             "torch.uint8": torch.uint8, "torch.int8": torch.int8, "torch.int64": torch.int64}
+
+
+def _reference_state_dict(case):
+    z = np.load(ROOT / "tests" / "golden" / "reference_state_dicts.npz")
+    sd, extra = {}, {}
+    for k in z.files:
+        if not k.startswith(case + "::"):
+            continue
+        name = k.split("::", 1)[1]
+        if name.startswith("__dtype__"):
+            continue
+        if name.startswith("__"):
+            extra[name] = z[k]
+            continue
+        dt = _TORCH_DT[str(z[f"{case}::__dtype__{name}"])]
+        arr = z[k]
+        t = torch.from_numpy(arr.view(np.int16).copy()).view(dt) if dt in (torch.bfloat16, torch.float16) else \
+            torch.from_numpy(arr.copy())
+        assert t.dtype == dt, (name, t.dtype, dt)
+        sd[name] = t
+    return sd, extra
+
+
+@pytest.mark.parametrize("case,qt,nested,storage", [
+    ("l4_nf4_plain", "nf4", False, torch.uint8), ("l4_nf4_nested", "nf4", True, torch.uint8),
+    ("l4_fp4_plain", "fp4", False, torch.uint8), ("l4_nf4_bf16storage", "nf4", False, torch.bfloat16)])
+def test_reference_linear4bit_checkpoint_round_trips(case, qt, nested, storage):
+    import bitsandbytes_b200 as bnb
+
+    ref_sd, extra = _reference_state_dict(case)
+    bs, is_nested, K, N = (int(v) for v in extra["__meta__"])
+    assert bool(is_nested) == nested
+    m = bnb.nn.Linear4bit(K, N, bias=True, compute_dtype=torch.bfloat16, compress_statistics=nested, quant_type=qt,
+                          quant_storage=storage)
+    # the route HF Transformers takes for a pre-quantised checkpoint (and reference tests/test_linear4bit.py:60-75):
+    # Params4bit.from_prequantized(data, quantized_stats) -- the reference's Linear4bit has no load hook either
+    stats = {k[len("weight."):]: v for k, v in ref_sd.items() if k.startswith("weight.")}
+    m.weight = bnb.nn.Params4bit.from_prequantized(data=ref_sd["weight"], quantized_stats=stats, device="cpu",
+                                                   module=m)
+    with torch.no_grad():
+        m.bias.copy_(ref_sd["bias"])
+    w = m.weight
+    assert w.bnb_quantized and w.quant_state is not None
+    qs = w.quant_state
+    assert (qs.blocksize, qs.quant_type, tuple(qs.shape), qs.nested) == (bs, qt, (N, K), nested)
+    assert qs.dtype == torch.float32  # the layer was quantised from an fp32 nn.Linear
+    assert w.dtype == storage and w.numel() * w.element_size() == N * K // 2
+    out_sd = m.state_dict()
+    assert set(out_sd) == set(ref_sd)
+    for k, v in ref_sd.items():
+        got = out_sd[k]
+        assert got.dtype == v.dtype and got.shape == v.shape, k
+        assert torch.equal(got.view(torch.uint8) if got.dtype != torch.uint8 else got,
+                           v.view(torch.uint8) if v.dtype != torch.uint8 else v), k
+
+
+def test_reference_linear8bitlt_checkpoint_round_trips():
+    import bitsandbytes_b200 as bnb
+
+    ref_sd, extra = _reference_state_dict("l8")
+    N, K = extra["__float_weight__"].shape
+    m = bnb.nn.Linear8bitLt(K, N, bias=True, has_fp16_weights=False, threshold=6.0)
+    with pytest.raises(RuntimeError, match="non-quantized Linear8bitLt"):  # the reference's rule (nn/modules.py:1111-1116)
+        m.load_state_dict(ref_sd, strict=True)
+    # a quantised (int8 + SCB) module accepts the checkpoint: on a GPU `.cuda()` puts it in that state, here the
+    # int8 parameter is installed directly, the way Transformers' bnb quantizer does for pre-quantised weights
+    m.weight = bnb.nn.Int8Params(torch.zeros(N, K, dtype=torch.int8), requires_grad=False, has_fp16_weights=False,
+                                 SCB=torch.zeros(N))
+    missing, unexpected = m.load_state_dict(ref_sd, strict=True)
+    assert not missing and not unexpected
+    assert m.weight.dtype == torch.int8 and torch.equal(m.weight.data, ref_sd["weight"])
+    assert m.weight.SCB is not None and torch.equal(m.weight.SCB, ref_sd["SCB"])
+    # the row statistics are the row absmax of the fp16-cast weight (reference Int8Params._quantize casts first)
+    W = torch.from_numpy(extra["__float_weight__"]).half()
+    assert torch.equal(W.abs().amax(dim=1).float(), ref_sd["SCB"])
+    out_sd = m.state_dict()
+    assert set(out_sd) == set(ref_sd)
+    for k, v in ref_sd.items():
+        assert out_sd[k].dtype == v.dtype and torch.equal(out_sd[k], v), k

@@ -89,6 +89,47 @@ def create_normal_map(offset: float = 0.9677083, use_extra_value: bool = True) -
     return vals / vals.max()
 
 
+def create_linear_map(signed: bool = True, total_bits: int = 8, add_zero: bool = True) -> Tensor:
+    """Evenly spaced code book on [-1, 1] (or [0, 1]); fewer than 8 bits are simulated by zero entries
+    in the middle of the 256-entry table, and a signed table then gives up one level so that it stays
+    centred on zero (reference functional.py:150-166; pinned against a golden copy)."""
+    levels = 2**total_bits
+    if signed and (add_zero or total_bits < 8):
+        levels -= 1
+    ramp = torch.linspace(-1.0 if signed else 0.0, 1.0, levels)
+    pad = 256 - ramp.numel()
+    if pad == 0:
+        return ramp
+    lower = ramp.numel() // 2
+    return torch.tensor(ramp[:lower].tolist() + [0.0] * pad + ramp[lower:].tolist(), dtype=torch.float32)
+
+
+def create_fp8_map(signed: bool = True, exponent_bits: int = 5, precision_bits: int = 2, total_bits: int = 8) -> Tensor:
+    """Code book of a small floating-point format (sign / exponent / fraction), normalised to max 1
+    and zero-padded to 256 entries: exponent field 0 holds the subnormals ``f * 2^-bias``, field
+    ``E > 0`` holds ``(1 + f) * 2^-(E - bias - 1)`` with ``bias = 2^(exponent_bits - 1)`` -- the
+    reference's convention, in which larger exponent fields mean SMALLER magnitudes (reference
+    functional.py:227-293; pinned against a golden copy)."""
+    if exponent_bits + precision_bits != total_bits - (1 if signed else 0):
+        raise AssertionError("sign + exponent + precision bits must add up to total_bits")
+    bias = 2 ** (exponent_bits - 1)
+    fractions = [sum(((m >> (precision_bits - 1 - i)) & 1) * 2.0 ** -(i + 1) for i in range(precision_bits))
+                 for m in range(2**precision_bits)]
+    values: list[float] = []
+    for field in range(2**exponent_bits):
+        for f in fractions:
+            v = f * 2.0**-bias if field == 0 else (1.0 + f) * 2.0 ** -(field - bias - 1)
+            values.append(v)
+            if signed:
+                values.append(-v)
+    if len(values) != 2**total_bits:
+        raise AssertionError("fp8 map size mismatch")
+    values += [0.0] * (256 - len(values))
+    values.sort()
+    code = torch.tensor(values, dtype=torch.float32)
+    return code / code.max()
+
+
 def get_4bit_type(typename: str, device=None, blocksize: int = 64) -> Tensor:
     """16 fp32 code values, normalised to max |v| == 1 (reference functional.py:772-859)."""
     if device is None:

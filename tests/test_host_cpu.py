@@ -557,3 +557,36 @@ def test_reference_linear8bitlt_checkpoint_round_trips():
     assert set(out_sd) == set(ref_sd)
     for k, v in ref_sd.items():
         assert out_sd[k].dtype == v.dtype and torch.equal(out_sd[k], v), k
+
+
+def _codebook_cases():
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    try:
+        import make_golden_codebooks as g
+    finally:
+        sys.path.pop(0)
+    return g
+
+
+def test_code_book_builders_match_the_reference_bit_for_bit():
+    """create_linear_map / create_fp8_map / create_dynamic_map / create_normal_map against goldens generated by the
+    reference for a spread of parameters (tests/golden/make_golden_codebooks.py)."""
+    import bitsandbytes_b200.functional as F
+
+    g = _codebook_cases()
+    z = np.load(ROOT / "tests" / "golden" / "reference_codebooks.npz")
+
+    def same(name, ours):
+        ref = z[name]
+        got = ours.numpy()
+        assert got.dtype == ref.dtype and got.shape == ref.shape, name
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (name, np.abs(got - ref).max())
+
+    for a in g.LINEAR:
+        same("linear_" + "_".join(str(int(v)) for v in a), F.create_linear_map(*a))
+    for a in g.FP8:
+        same("fp8_" + "_".join(str(int(v)) for v in a), F.create_fp8_map(*a))
+    for a in g.DYNAMIC:
+        same("dynamic_" + "_".join(str(int(v)) for v in a), F.create_dynamic_map(*a))
+    for off, extra in g.NORMAL:
+        same(f"normal_{off}_{int(extra)}", F.create_normal_map(off, extra))

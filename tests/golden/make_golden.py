@@ -108,7 +108,23 @@ def make_inputs():
         torch.rand(24) * 2 + 0.1,
         torch.randn(24).half(),
     )
+    # later additions draw AFTER everything above, so the earlier cases keep their values
+    for name, n, bs in (("d", 1, 256), ("e", 255, 256), ("f", 4096 * 3, 512), ("g", 70001, 2048), ("h", 129, 64)):
+        inp[f"q8_{name}"] = (torch.randn(n, dtype=torch.float32) * (10.0 if name == "g" else 1.0), bs)
+    for name, shape, bs, dt in (
+        ("d", (1,), 64, torch.float32),
+        ("e", (63,), 64, torch.bfloat16),
+        ("f", (3, 1000), 256, torch.float16),
+        ("g", (16, 4096), 4096, torch.bfloat16),
+        ("h", (130,), 32, torch.float32),
+        ("i", (5, 512), 512, torch.float32),
+    ):
+        inp[f"q4_{name}"] = (torch.randn(*shape, dtype=torch.float32).to(dt), bs, shape, dt)
     return inp
+
+
+Q8_NAMES = ("a", "b", "c", "d", "e", "f", "g", "h")
+Q4_NAMES = ("a", "b", "c", "d", "e", "f", "g", "h", "i")
 
 
 def phase(which: str, out_path: str):
@@ -124,7 +140,7 @@ def phase(which: str, out_path: str):
         out["nf4_code"] = F.get_4bit_type("nf4", device="cpu").numpy()
         out["fp4_code"] = F.get_4bit_type("fp4", device="cpu").numpy()
 
-    for name in ("a", "b", "c"):
+    for name in Q8_NAMES:
         A, bs = inp[f"q8_{name}"]
         q, absmax = ops.quantize_blockwise(A, code, bs)
         key = f"q8_{name}"
@@ -142,7 +158,7 @@ def phase(which: str, out_path: str):
             out[f"{key}_deq_{DT_NAME[dt]}_{which}"] = bits(d)
 
     for qt in ("nf4", "fp4"):
-        for name in ("a", "b", "c"):
+        for name in Q4_NAMES:
             A, bs, shape, dt = inp[f"q4_{name}"]
             key = f"q4_{qt}_{name}"
             packed, absmax = ops.quantize_4bit(A, bs, qt, torch.uint8)  # default impl in both phases

@@ -38,6 +38,12 @@ def _assert_bits_equal(got, want, dtype, fp4_zero=False):
     np.testing.assert_array_equal(got, want)
 
 
+# cases of tests/golden/make_golden.py: a-c the original ones, d-i edge sizes (1 element, one short of a block,
+# ragged tails, blocksize 32 ... 4096)
+Q8_NAMES = ["a", "b", "c", "d", "e", "f", "g", "h"]
+Q4_NAMES = ["a", "b", "c", "d", "e", "f", "g", "h", "i"]
+
+
 def test_codebooks(golden):
     np.testing.assert_array_equal(oracle.lut4("nf4"), golden["nf4_code"])
     np.testing.assert_array_equal(oracle.lut4("fp4"), golden["fp4_code"])
@@ -45,7 +51,7 @@ def test_codebooks(golden):
     assert np.signbit(oracle.lut4("fp4")[8])
 
 
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", Q8_NAMES)
 def test_quantize_8bit_vs_reference_default(golden, name):
     A = golden[f"q8_{name}_A"]
     bs = int(golden[f"q8_{name}_bs"])
@@ -62,7 +68,7 @@ def test_quantize_8bit_vs_reference_default(golden, name):
     assert bad.size <= max(2, A.size // 5000)
 
 
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", Q8_NAMES)
 @pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("which", ["default", "native"])
 def test_dequantize_8bit_bit_exact(golden, name, dtype, which):
@@ -79,7 +85,7 @@ def test_dequantize_8bit_bit_exact(golden, name, dtype, which):
 
 
 @pytest.mark.parametrize("qt", ["nf4", "fp4"])
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", Q4_NAMES)
 def test_quantize_4bit_vs_reference_default(golden, qt, name):
     key = f"q4_{qt}_{name}"
     dt = str(golden[f"{key}_dtype"])
@@ -118,7 +124,7 @@ def test_quantize_4bit_vs_reference_default(golden, qt, name):
 
 
 @pytest.mark.parametrize("qt", ["nf4", "fp4"])
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", Q4_NAMES)
 @pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("which", ["default", "native"])
 def test_dequantize_4bit_bit_exact(golden, qt, name, dtype, which):

@@ -208,3 +208,29 @@ def test_reference_cpu_library_direct():
             fn(packed.ctypes.data, absmax.ctypes.data, out.ctypes.data, bs, n // 64, 64)
             want = oracle.dequantize_blockwise(packed, absmax, bs, n, qt, None, dtype)
             _assert_bits_equal(out, want, dtype, fp4_zero=(qt == "fp4"))
+
+
+# The same checker the GPU suite runs over the golden vectors (tests/_golden_check.py), here with the
+# oracle as the implementation: validates the checker and pins the oracle once more.
+def _oracle_quantize(A, dtype, bs, qt, code):
+    a = A if dtype == "fp32" else oracle.widen(A.reshape(-1), dtype)
+    return oracle.quantize_blockwise(np.ascontiguousarray(a, dtype=np.float32), bs, qt, code)
+
+
+def _oracle_dequantize(codes, absmax, bs, n, qt, code, out_dtype):
+    return oracle.dequantize_blockwise(codes, absmax, bs, n, qt, code, out_dtype)
+
+
+@pytest.mark.parametrize("name", Q8_NAMES)
+def test_golden_checker_8bit_with_the_oracle(name):
+    from tests import _golden_check as gc
+
+    gc.check_8bit(gc.load(), name, _oracle_quantize, _oracle_dequantize)
+
+
+@pytest.mark.parametrize("qt", ["nf4", "fp4"])
+@pytest.mark.parametrize("name", Q4_NAMES)
+def test_golden_checker_4bit_with_the_oracle(qt, name):
+    from tests import _golden_check as gc
+
+    gc.check_4bit(gc.load(), qt, name, _oracle_quantize, _oracle_dequantize)

@@ -75,3 +75,48 @@ def check_4bit(z, qt, name, quantize_fn, dequantize_fn):
         want = z[f"{key}_deq_{dt}_default"].reshape(-1)
         np.testing.assert_array_equal(_canon_zero(_as_bits(got).reshape(-1)), _canon_zero(_as_bits(want)),
                                       err_msg=f"dequantize_4bit -> {dt} must be bit-exact")
+
+
+GEMM4_NAMES = ["plain", "nested", "fp16"]
+
+
+def check_gemm4(z, name, gemm_fn):
+    """gemm_fn(x_bits u16, dtype, packed u8, absmax f32, absmax_8bit u8|None, absmax_code f32|None,
+    absmax_offset float|None, bias_bits u16|None, M, N, K, blocksize, qt) -> [M, N] float64 values of T.
+    The golden output is the reference's public API on its CPU backend (dequantize + F.linear in T):
+    two roundings of the same exact sums, so within two T-ulps of each other."""
+    key = f"gemm4_{name}"
+    M, N, K = (int(v) for v in z[f"{key}_shape"])
+    qt = str(z[f"{key}_qt"])
+    dt = str(z[f"{key}_dtype"])
+    nested = f"{key}_absmax8" in z.files
+    absmax = z[f"{key}_absmax2"] if nested else z[f"{key}_absmax"]
+    a8 = z[f"{key}_absmax8"] if nested else None
+    code2 = z[f"{key}_code2"] if nested else None
+    offset = float(z[f"{key}_offset"][0]) if nested else None
+    bias = z[f"{key}_bias"] if f"{key}_bias" in z.files else None
+    got = gemm_fn(z[f"{key}_x"].reshape(-1), dt, z[f"{key}_packed"], absmax, a8, code2, offset, bias, M, N, K, 64, qt)
+    got = np.asarray(got, dtype=np.float64).reshape(M, N)
+    y_bits = z[f"{key}_y"].reshape(-1)
+    if dt == "bf16":
+        y_ref = (y_bits.astype(np.uint32) << 16).view(np.float32).astype(np.float64).reshape(M, N)
+        eps = 2.0**-8
+    else:
+        y_ref = y_bits.view(np.float16).astype(np.float64).reshape(M, N)
+        eps = 2.0**-11
+    assert np.all(np.isfinite(got))
+    err = np.abs(got - y_ref)
+    assert np.all(err <= 2 * eps * np.abs(y_ref) + 4e-3), float(err.max())
+
+
+def check_int8_gemm(z, gemm_fn, dequant_fn):
+    """gemm_fn(A i8 [M,K], B i8 [N,K]) -> int32 [M,N] (exact); dequant_fn(C i32, row_stats, col_stats, bias_bits|None)
+    -> fp16 bit patterns [M,N], within one fp16 ulp of the reference's pure-torch kernel (which multiplies by
+    1/127^2 in a different order)."""
+    C = gemm_fn(z["i8mm_A"], z["i8mm_B"])
+    np.testing.assert_array_equal(C, z["i8mm_C"])
+    for tag, bias in (("nobias", None), ("bias", z["i8mm_bias"])):
+        got = np.asarray(dequant_fn(z["i8mm_C"], z["i8mm_rs"], z["i8mm_cs"], bias)).reshape(-1).view(np.float16)
+        want = z[f"i8mm_deq_{tag}"].reshape(-1).view(np.float16)
+        ulp = np.spacing(np.abs(want)).astype(np.float32)
+        assert np.all(np.abs(got.astype(np.float32) - want.astype(np.float32)) <= ulp + 1e-7)

@@ -234,3 +234,25 @@ def test_golden_checker_4bit_with_the_oracle(qt, name):
     from tests import _golden_check as gc
 
     gc.check_4bit(gc.load(), qt, name, _oracle_quantize, _oracle_dequantize)
+
+
+def _oracle_gemm4(x_bits, dt, packed, absmax, a8, code2, offset, bias_bits, M, N, K, bs, qt):
+    kw = {}
+    if a8 is not None:
+        kw = dict(absmax_8bit=a8, absmax_code=code2, absmax_offset=offset)
+    bias = oracle.widen(bias_bits, dt) if bias_bits is not None else None
+    y64 = oracle.gemm_4bit(oracle.widen(x_bits, dt), packed, absmax, M, N, K, bs, qt, dt, bias, **kw)
+    return oracle.widen(oracle.round_to(np.asarray(y64, dtype=np.float32), dt), dt).astype(np.float64)
+
+
+@pytest.mark.parametrize("name", ["plain", "nested", "fp16"])
+def test_golden_checker_gemm4_with_the_oracle(name):
+    from tests import _golden_check as gc
+
+    gc.check_gemm4(gc.load(), name, _oracle_gemm4)
+
+
+def test_golden_checker_int8_with_the_oracle():
+    from tests import _golden_check as gc
+
+    gc.check_int8_gemm(gc.load(), oracle.int8_gemm, oracle.int8_mm_dequant)

@@ -590,3 +590,19 @@ def test_code_book_builders_match_the_reference_bit_for_bit():
         same("dynamic_" + "_".join(str(int(v)) for v in a), F.create_dynamic_map(*a))
     for off, extra in g.NORMAL:
         same(f"normal_{off}_{int(extra)}", F.create_normal_map(off, extra))
+
+
+def test_fused_forward_rejects_a_mismatched_gather_buffer_before_any_launch():
+    """parallel.fused_forward validates the symmetric-memory slot against the layer on the host."""
+    from types import SimpleNamespace
+
+    from bitsandbytes_b200 import parallel
+
+    shard = parallel.Shard4bit(packed=torch.zeros(8 * 64 // 2, dtype=torch.uint8), absmax=torch.zeros(8), absmax_8bit=None,
+                               absmax_code=None, absmax_offset=None, rows=8, row0=0, K=64, blocksize=64, quant_type="nf4")
+    layer = parallel.ColumnParallelLinear4bit(shard, out_features=16)
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    for peers in (SimpleNamespace(M=5, N=16, dtype=torch.bfloat16), SimpleNamespace(M=4, N=32, dtype=torch.bfloat16),
+                  SimpleNamespace(M=4, N=16, dtype=torch.float16)):
+        with pytest.raises(ValueError, match="different output shape"):
+            parallel.fused_forward(layer, x, peers)

@@ -85,9 +85,19 @@ template <> struct TcFmt<__half> { static constexpr uint32_t kFmt = 0; };
 // shared memory and 64 TMEM columns of decoded weights.  One `full` and one `empty` mbarrier per
 // stage keep the synchronisation cost on the single MMA-issuing thread at one wait + one commit
 // per eight tcgen05.mma (it was the bottleneck with 64-wide stages and separate barriers).
-template <int MT> struct StageCfg {
-    static constexpr int kStages = (MT == 256) ? 3 : 4;          // smem: kStages * (MT * 256 + 8192) B <= 216 KB
-    static constexpr int kXSubBytes = MT * 128;                  // one 64-wide sub-tile
+//
+// PAIR (cta_group::2, BNB_B200_PAIR=1, measured in round 1: bit-identical, 148 us vs 130 us at 4096^3):
+// the two CTAs of a cluster own adjacent 128-feature tiles of the SAME token tile.  One tcgen05.mma
+// issued by the leader drives both SMs (M = 256: 128 decoded rows from each CTA's TMEM); the
+// activation tile is split between the two shared memories (MT/2 tokens each), so every SM ingests
+// half the activation bytes: 40 KB per stage instead of 72 KB at MT = 256.  72 KB per 1024 MMA cycles
+// is 70 B/clk against the ~41 B/clk/SM the L2 -> SM path sustains (11.5 TB/s chip-wide), which is
+// the 0.6 roofline fraction of the single-CTA kernel; the pair removes that bound but its decode ->
+// MMA hand-off crosses SMs every stage and needs a redesign before it wins.
+template <int MT, bool PAIR = false> struct StageCfg {
+    static constexpr int kXRows = PAIR ? MT / 2 : MT;            // token rows staged by this CTA
+    static constexpr int kStages = (MT == 256 && !PAIR) ? 3 : 4; // smem: kStages * (kXRows * 256 + 8192) B <= 216 KB
+    static constexpr int kXSubBytes = kXRows * 128;              // one 64-wide sub-tile
     static constexpr int kXStageBytes = 2 * kXSubBytes;
     static constexpr int kWStageBytes = kTileN * 64;             // packed codes: 128 rows x 64 B (TMA, 64-B swizzle)
     static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
@@ -96,11 +106,12 @@ template <int MT> struct StageCfg {
     static_assert(kWCol0 + kStages * 64 <= kTmemCols, "TMEM budget");
 };
 
-template <typename T, int QT, int MT, int CL>
+template <typename T, int QT, int MT, int CL, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const Gemm4Params p) {
-    using Cfg = StageCfg<MT>;
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    using Cfg = StageCfg<MT, PAIR>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kXSubBytes = Cfg::kXSubBytes;
     constexpr int kXStageBytes = Cfg::kXStageBytes;
@@ -155,16 +166,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(&full[s], 1 + kDecodeWarps / 2);
-            ptx::mbar_init(&empty[s], CL);
+            // pair, leader: + one relayed arrival for the peer's decode group, and the activation bytes of
+            // both CTAs; pair, peer: full[s] only collects its own decode group for the relay (warp 1)
+            ptx::mbar_init(&full[s], PAIR ? (ptx::cluster_ctarank() == 0 ? 2 + kDecodeWarps / 2 : kDecodeWarps / 2)
+                                          : 1 + kDecodeWarps / 2);
+            ptx::mbar_init(&empty[s], PAIR ? 1 : CL);
             ptx::mbar_init(&w_full[s], 1);
         }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc<kTmemCols>(tmem_slot);
-        ptx::tmem_relinquish();
+        if constexpr (PAIR) {
+            ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc<kTmemCols>(tmem_slot);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     if constexpr (CL > 1) {
@@ -183,7 +202,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait(&empty[s], ph ^ 1u);  // every CTA of the cluster has consumed this stage
+                if constexpr (PAIR) {
+                    ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, i);
+                } else {
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);  // every CTA of the cluster has consumed this stage
+                }
                 const int k0 = (st_begin + i) * kBK;
                 if (p.debug & 32) {
                     ptx::mbar_arrive(&w_full[s]);
@@ -192,7 +215,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ptx::mbar_arrive_expect_tx(&w_full[s], kWStageBytes);
                     ptx::tma_load_2d(sw + s * kWStageBytes, &tmap_w, &w_full[s], k0 / 2, n0);
                 }
-                if (p.debug & 4) {
+                if constexpr (PAIR) {
+                    // this CTA stages tokens [rank*MT/2, +MT/2) in its OWN shared memory; the bytes of both
+                    // CTAs complete on the leader's barrier, which the leader's producer arms for both
+                    const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kXStageBytes);
+                    uint8_t* dst = sx + s * kXStageBytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        ptx::tma_load_2d_pair(dst + h * kXSubBytes, &tmap_x, lead_full, k0 + 64 * h,
+                                              m0 + (int)cta_rank * (MT / 2));
+                } else if (p.debug & 4) {
                     ptx::mbar_arrive(&full[s]);
                 } else {
                     ptx::mbar_arrive_expect_tx(&full[s], kXStageBytes);
@@ -220,11 +253,33 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
-        constexpr uint32_t idesc = ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/128, /*N=*/MT);
+        constexpr uint32_t idesc =
+            ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/PAIR ? 256 : 128, /*N=*/MT);
         int s = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < nst; ++i) {
-            ptx::mbar_wait(&full[s], ph);
+        if (PAIR && cta_rank != 0) {
+            // peer of a pair: this warp does not issue MMAs (the leader's drive both SMs).  It relays
+            // "my decode group has filled TMEM slot s" to the leader's barrier with ONE cluster-scope
+            // arrive per stage, so that the 16 decode warps only ever pay CTA-scope arrives
+            // (178 -> 148 us at 4096^3 when every decode warp arrived remotely).
+            for (int i = 0; i < nst; ++i) {
+                ptx::mbar_wait_bounded(&full[s], ph, 6, i);
+                if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&full[s]), 0));
+                __syncwarp();
+                if (++s == kStages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+        // pair: only the leader issues; its instructions drive the tensor cores of both SMs
+        const int nst_mma = (PAIR && cta_rank != 0) ? 0 : nst;
+        for (int i = 0; i < nst_mma; ++i) {
+            if constexpr (PAIR) {
+                ptx::mbar_wait_bounded(&full[s], ph, 2, i);
+            } else {
+                ptx::mbar_wait(&full[s], ph);
+            }
             ptx::tc_fence_after();
             if (lane == 0) {
                 const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
@@ -235,16 +290,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         // K advances by 16 elements: +8 TMEM columns for A, +32 B (2 x 16 B) inside a sub-tile
-                        ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3), idesc,
-                                        (i | j) != 0 ? 1u : 0u);
+                        if constexpr (PAIR)
+                            ptx::mma_f16_ts_pair(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3),
+                                                 idesc, (i | j) != 0 ? 1u : 0u);
+                        else
+                            ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3), idesc,
+                                            (i | j) != 0 ? 1u : 0u);
                     }
                 }
-                if constexpr (CL == 1) {
+                if constexpr (PAIR) {
+                    ptx::tc_commit_pair(&empty[s], kClusterMask);
+                    if (i == nst - 1) ptx::tc_commit_pair(acc_full, kClusterMask);
+                } else if constexpr (CL == 1) {
                     ptx::tc_commit(&empty[s]);
+                    if (i == nst - 1) ptx::tc_commit(acc_full);
                 } else {
                     ptx::tc_commit_multicast(&empty[s], kClusterMask);
+                    if (i == nst - 1) ptx::tc_commit(acc_full);
                 }
-                if (i == nst - 1) ptx::tc_commit(acc_full);
             }
             __syncwarp();
             if (++s == kStages) {
@@ -301,7 +364,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float sc0 = wsc[j][0], sc1 = wsc[j][1];
                     fetch(j, t + kScaleDepth);
 
-                    ptx::mbar_wait(&w_full[s], ph);  // this stage's codes have landed
+                    if constexpr (PAIR) {
+                        ptx::mbar_wait_bounded(&w_full[s], ph, 3, i);
+                    } else {
+                        ptx::mbar_wait(&w_full[s], ph);  // this stage's codes have landed
+                    }
                     const uint8_t* wt = sw + s * kWStageBytes + sw_row;
                     const uint4 q0 = *reinterpret_cast<const uint4*>(wt + sw_c0);
                     const uint4 q1 = *reinterpret_cast<const uint4*>(wt + sw_c1);
@@ -328,7 +395,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
                     // w_full[s] completing implies the producer saw empty[s]; waiting on it here as well
                     // makes this warp itself an observer of the MMA completion before it overwrites TMEM.
-                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    if constexpr (PAIR) {
+                        ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 4, i);
+                    } else {
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    }
                     ptx::tc_fence_after();
                     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 64 + half * 32;
                     if (!(p.debug & 2)) {
@@ -343,7 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
 
         // ================================================================== epilogue
-        ptx::mbar_wait(acc_full, 0);
+        if constexpr (PAIR) {
+            ptx::mbar_wait_bounded(acc_full, 0, 5);
+        } else {
+            ptx::mbar_wait(acc_full, 0);
+        }
         ptx::tc_fence_after();
 
         // this warp: lanes [quarter*32, +32) (= output features), columns [khalf*MT/2, +MT/2)
@@ -454,7 +529,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
+        if constexpr (PAIR)
+            ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+        else
+            ptx::tmem_dealloc_dyn(tmem_base, kTmemCols);
     }
 }
 
@@ -793,11 +871,12 @@ int cluster_override() {
     return v;
 }
 
-template <typename T, int QT, int MT, int CL>
+template <typename T, int QT, int MT, int CL, bool PAIR = false>
 bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
-    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(StageCfg<MT>::kStages) * StageCfg<MT>::kStageBytes + 256 /*barriers*/;
+    using Cfg = StageCfg<MT, PAIR>;
+    constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(Cfg::kStages) * Cfg::kStageBytes + 256 /*barriers*/;
     static bool attr_set = false;
-    auto kern = gemm4_tc_kernel<T, QT, MT, CL>;
+    auto kern = gemm4_tc_kernel<T, QT, MT, CL, PAIR>;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("gemm4_tc smem attr", cudaGetLastError());
@@ -851,7 +930,7 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     const int tiles = n_tiles * m_tiles;
 
     // Experimental persistent variant (see gemm4_tc_persistent_kernel): more tiles than SMs, no clusters.
-    if constexpr (CL == 1 && MT >= 128) {
+    if constexpr (CL == 1 && MT >= 128 && !PAIR) {
         if (persistent_enabled() && tiles > sms) {
             static bool pattr_set = false;
             auto pkern = gemm4_tc_persistent_kernel<T, QT, MT>;
@@ -997,6 +1076,13 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     const int ov = cluster_override();
     if (ov == 1 || (ov == 2 && n_tiles % 2 == 0 && MT >= 128) || (ov == 4 && n_tiles % 4 == 0 && MT >= 128)) CL = ov;
 
+    // CTA pairs (cta_group::2) for the large-M tile: BNB_B200_PAIR=1 (measured slower in round 1; off)
+    static const bool pair_env = [] {
+        const char* e = getenv("BNB_B200_PAIR");
+        return e != nullptr && e[0] == '1';
+    }();
+    const bool pair = pair_env && MT == 256 && n_tiles % 2 == 0;
+
 #define BNB200_DISPATCH_MT(QT)                                                                                         \
     switch (MT) {                                                                                                      \
     case 16: return launch_mt<T, QT, 16, 1>(A, p, stream);                                                             \
@@ -1007,6 +1093,7 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
         if (CL == 2) return launch_mt<T, QT, 128, 2>(A, p, stream);                                                    \
         return launch_mt<T, QT, 128, 1>(A, p, stream);                                                                 \
     default:                                                                                                           \
+        if (pair) return launch_mt<T, QT, 256, 2, true>(A, p, stream);                                                 \
         if (CL == 4) return launch_mt<T, QT, 256, 4>(A, p, stream);                                                    \
         if (CL == 2) return launch_mt<T, QT, 256, 2>(A, p, stream);                                                    \
         return launch_mt<T, QT, 256, 1>(A, p, stream);                                                                 \

@@ -253,6 +253,18 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask)
                  : "memory");
 }
 
+// D[tmem, both CTAs] (+)= A[tmem, per CTA] * B[smem desc, half per CTA]   (kind::f16, M = 256)
+__device__ __forceinline__ void mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "}\n" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+
 // D[tmem, both CTAs] (+)= A[smem desc, per CTA] * B[smem desc, half per CTA]   (kind::i8, M = 256)
 __device__ __forceinline__ void mma_i8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                uint32_t accumulate) {

@@ -106,7 +106,12 @@ template <int MT, bool PAIR = false> struct StageCfg {
     static_assert(kWCol0 + kStages * 64 <= kTmemCols, "TMEM budget");
 };
 
-template <typename T, int QT, int MT, int CL, bool PAIR>
+// D16 (BNB_B200_DECODE16=1, experimental, written at the end of round 1 and not yet run): all 16 decode
+// warps work on EVERY stage (each thread 32 codes of its row, one tcgen05.st.x16) instead of two
+// groups of 8 that alternate stages.  The table of a 64-element quantisation block is then built by
+// two threads (+14 % decode instructions), but a stage is decoded in one stage time instead of two,
+// which is what the pair variant's cross-SM hand-off needs.
+template <typename T, int QT, int MT, int CL, bool PAIR, bool D16>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const Gemm4Params p) {
@@ -168,8 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int s = 0; s < kStages; ++s) {
             // pair, leader: + one relayed arrival for the peer's decode group, and the activation bytes of
             // both CTAs; pair, peer: full[s] only collects its own decode group for the relay (warp 1)
-            ptx::mbar_init(&full[s], PAIR ? (ptx::cluster_ctarank() == 0 ? 2 + kDecodeWarps / 2 : kDecodeWarps / 2)
-                                          : 1 + kDecodeWarps / 2);
+            constexpr int kArrivers = D16 ? kDecodeWarps : kDecodeWarps / 2;  // decode warps per stage
+            ptx::mbar_init(&full[s], PAIR ? (ptx::cluster_ctarank() == 0 ? 2 + kArrivers : kArrivers) : 1 + kArrivers);
             ptx::mbar_init(&empty[s], PAIR ? 1 : CL);
             ptx::mbar_init(&w_full[s], 1);
         }
@@ -335,6 +340,47 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t sw_c0 = (uint32_t)(((2 * half) ^ ((row >> 1) & 3)) * 16);
         const uint32_t sw_c1 = (uint32_t)(((2 * half + 1) ^ ((row >> 1) & 3)) * 16);
 
+        if constexpr (D16) {
+            // ---- every decode warp on every stage: thread = (row, 32 consecutive k)
+            const int kq = dw >> 2;  // which 32 of the stage's 128 k-elements
+            const uint32_t sw_c = (uint32_t)((kq ^ ((row >> 1) & 3)) * 16);
+            float wsc1[kScaleDepth];
+            auto fetch1 = [&](int j, int stage_idx) {
+                wsc1[j] = 0.f;
+                const int kb32 = 4 * (st_begin + stage_idx) + kq;  // 32-wide k-block of this thread
+                if (stage_idx < nst && n_ok && kb32 * 32 < p.K) wsc1[j] = sc.load((e_row + (long long)kb32 * 32) >> p.log2_bs);
+            };
+#pragma unroll
+            for (int j = 0; j < kScaleDepth; ++j) fetch1(j, j);
+            for (int i0 = 0; i0 < nst; i0 += kScaleDepth) {
+#pragma unroll
+                for (int j = 0; j < kScaleDepth; ++j) {
+                    const int i = i0 + j;
+                    if (i < nst) {
+                        const int s = i % kStages;
+                        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+                        const float sc0 = wsc1[j];
+                        fetch1(j, i + kScaleDepth);
+                        ptx::mbar_wait_bounded(&w_full[s], ph, 23, i);
+                        const uint4 q = *reinterpret_cast<const uint4*>(sw + s * kWStageBytes + sw_row + sw_c);
+                        uint32_t r[16];
+                        DecodeTable tab;
+                        build_table<T, QT>(sc0, tab);
+                        decode_word(q.x, tab, r + 0);
+                        decode_word(q.y, tab, r + 4);
+                        decode_word(q.z, tab, r + 8);
+                        decode_word(q.w, tab, r + 12);
+                        ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 24, i);
+                        ptx::tc_fence_after();
+                        ptx::tmem_st_x16(tmem_base + (uint32_t(quarter * 32) << 16) + kWCol0 + s * 64 + kq * 16, r);
+                        ptx::tmem_wait_st();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        } else {
         // Scales are scattered 4-byte loads (one row per lane): a register ring kScaleDepth stages
         // deep hides their latency.  The loop is unrolled by the ring depth so that slot j is a fixed
         // register (no rotation: a move out of a load's destination would wait for the load).
@@ -412,6 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
         }
+
+        }  // !D16
 
         // ================================================================== epilogue
         if constexpr (PAIR) {
@@ -871,12 +919,12 @@ int cluster_override() {
     return v;
 }
 
-template <typename T, int QT, int MT, int CL, bool PAIR = false>
+template <typename T, int QT, int MT, int CL, bool PAIR = false, bool D16 = false>
 bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     using Cfg = StageCfg<MT, PAIR>;
     constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(Cfg::kStages) * Cfg::kStageBytes + 256 /*barriers*/;
     static bool attr_set = false;
-    auto kern = gemm4_tc_kernel<T, QT, MT, CL, PAIR>;
+    auto kern = gemm4_tc_kernel<T, QT, MT, CL, PAIR, D16>;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("gemm4_tc smem attr", cudaGetLastError());
@@ -930,7 +978,7 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     const int tiles = n_tiles * m_tiles;
 
     // Experimental persistent variant (see gemm4_tc_persistent_kernel): more tiles than SMs, no clusters.
-    if constexpr (CL == 1 && MT >= 128 && !PAIR) {
+    if constexpr (CL == 1 && MT >= 128 && !PAIR && !D16) {
         if (persistent_enabled() && tiles > sms) {
             static bool pattr_set = false;
             auto pkern = gemm4_tc_persistent_kernel<T, QT, MT>;
@@ -1077,11 +1125,11 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     if (ov == 1 || (ov == 2 && n_tiles % 2 == 0 && MT >= 128) || (ov == 4 && n_tiles % 4 == 0 && MT >= 128)) CL = ov;
 
     // CTA pairs (cta_group::2) for the large-M tile: BNB_B200_PAIR=1 (measured slower in round 1; off)
-    static const bool pair_env = [] {
-        const char* e = getenv("BNB_B200_PAIR");
-        return e != nullptr && e[0] == '1';
-    }();
-    const bool pair = pair_env && MT == 256 && n_tiles % 2 == 0;
+    // (both switches are read per call so that one process can A/B them: tools/probe_pair.py)
+    const char* pair_e = getenv("BNB_B200_PAIR");
+    const bool pair = pair_e != nullptr && pair_e[0] == '1' && MT == 256 && n_tiles % 2 == 0;
+    const char* d16_e = getenv("BNB_B200_DECODE16");
+    const bool d16 = d16_e != nullptr && d16_e[0] == '1';  // experimental, not yet run: off
 
 #define BNB200_DISPATCH_MT(QT)                                                                                         \
     switch (MT) {                                                                                                      \
@@ -1093,7 +1141,9 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
         if (CL == 2) return launch_mt<T, QT, 128, 2>(A, p, stream);                                                    \
         return launch_mt<T, QT, 128, 1>(A, p, stream);                                                                 \
     default:                                                                                                           \
+        if (pair && d16) return launch_mt<T, QT, 256, 2, true, true>(A, p, stream);                                    \
         if (pair) return launch_mt<T, QT, 256, 2, true>(A, p, stream);                                                 \
+        if (d16 && CL == 1) return launch_mt<T, QT, 256, 1, false, true>(A, p, stream);                                \
         if (CL == 4) return launch_mt<T, QT, 256, 4>(A, p, stream);                                                    \
         if (CL == 2) return launch_mt<T, QT, 256, 2>(A, p, stream);                                                    \
         return launch_mt<T, QT, 256, 1>(A, p, stream);                                                                 \

@@ -321,11 +321,14 @@ def main():
         # the SAME load running, untimed, until the sampler holds a handful of readings under load.
         t_stop = time.perf_counter() + 2.5
         j = 0
-        while len(clocks.samples) < 6 and time.perf_counter() < t_stop:
-            for _ in range(64):
-                step(j)
-                j += 1
-            torch.cuda.synchronize()
+        try:
+            while len(clocks.samples) < 6 and time.perf_counter() < t_stop:
+                for _ in range(64):
+                    step(j)
+                    j += 1
+                torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001  (the continuation only feeds the clock sampler)
+            print(f"[bench] clock-sampling continuation stopped: {exc!r}", file=sys.stderr)
         clock_extra_steps = j
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))

@@ -200,41 +200,3 @@ def test_c2_weight_quantize_properties(qt):
     if ref is not None:
         rq, rabs = nat.quantize(ref, W.view(-1), 64, qt, None, "bf16")
         assert torch.equal(rabs, absmax) and torch.equal(rq, q)
-
-
-# ---------------------------------------------------------------------------- golden vectors
-# The reference-generated fixtures (tests/golden/reference_vectors.npz: the reference's own CPU
-# backend and pure-torch kernels on seeded inputs, edge sizes included) through the product's C ABI.
-def _gpu_quantize(A, dtype, bs, qt, code):
-    if dtype == "fp32":
-        t = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float32).reshape(-1).copy())
-    else:
-        t = torch.from_numpy(np.ascontiguousarray(A).reshape(-1).view(np.int16).copy()).view(nat.DTYPE[dtype])
-    c = torch.from_numpy(code.copy()).cuda() if code is not None else None
-    out, absmax = nat.quantize(nat.lib, t.cuda(), bs, qt, c, dtype)
-    nat.check()
-    return out.cpu().numpy(), absmax.cpu().numpy()
-
-
-def _gpu_dequantize(codes, absmax, bs, n, qt, code, out_dtype):
-    c = torch.from_numpy(code.copy()).cuda() if code is not None else None
-    d = nat.dequantize(nat.lib, torch.from_numpy(np.ascontiguousarray(codes).copy()).cuda(),
-                       torch.from_numpy(np.ascontiguousarray(absmax).copy()).cuda(), bs, n, qt, c, out_dtype)
-    nat.check()
-    d = d.cpu()
-    return d.numpy() if out_dtype == "fp32" else d.view(torch.int16).numpy().view(np.uint16)
-
-
-@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f", "g", "h"])
-def test_golden_vectors_8bit(name):
-    from tests import _golden_check as gc
-
-    gc.check_8bit(gc.load(), name, _gpu_quantize, _gpu_dequantize)
-
-
-@pytest.mark.parametrize("qt", ["nf4", "fp4"])
-@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f", "g", "h", "i"])
-def test_golden_vectors_4bit(qt, name):
-    from tests import _golden_check as gc
-
-    gc.check_4bit(gc.load(), qt, name, _gpu_quantize, _gpu_dequantize)

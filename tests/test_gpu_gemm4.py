@@ -275,28 +275,3 @@ def test_legacy_gemv_entry_point():
     torch.cuda.synchronize()
     nat.check()
     assert_close_to_exact(out.view(1, 256), exact(p), "bf16", 512)
-
-
-# ---------------------------------------------------------------------------- golden vectors
-def _gpu_gemm4(x_bits, dt, packed, absmax, a8, code2, offset, bias_bits, M, N, K, bs, qt):
-    x = nat.from_bits(x_bits, dt).reshape(M, K)
-    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a).copy()).cuda()  # noqa: E731
-    off = None if offset is None else torch.tensor([offset], dtype=torch.float32, device="cuda")
-    bias = None if bias_bits is None else nat.from_bits(bias_bits, dt)
-    out = nat.gemm_4bit(nat.lib, x, t(packed), t(absmax), M, N, K, bs, qt, dt, bias, t(a8), t(code2), off)
-    nat.check()
-    return out.double().cpu().numpy()
-
-
-@pytest.mark.parametrize("path", [-1, 1], ids=["auto", "tcgen05"])
-@pytest.mark.parametrize("name", ["plain", "nested", "fp16"])
-def test_golden_vectors_gemm4(name, path):
-    """The reference's public API on its CPU backend (tests/golden/reference_vectors.npz) vs the product kernels
-    (the decode kernel by default at these M; the tcgen05 kernel when forced)."""
-    from tests import _golden_check as gc
-
-    nat.lib.cbnb_b200_gemm_4bit_force_path(path)
-    try:
-        gc.check_gemm4(gc.load(), name, _gpu_gemm4)
-    finally:
-        nat.lib.cbnb_b200_gemm_4bit_force_path(-1)

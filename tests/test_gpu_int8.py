@@ -147,37 +147,3 @@ def test_fused_scaled_mm_equals_gemm_then_dequant(M, N, K, with_bias):
                                    nat.stream())
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int16), want.view(torch.int16))
-
-
-# ---------------------------------------------------------------------------- golden vectors
-def test_golden_vectors_int8_gemm_and_dequant():
-    """tests/golden/reference_vectors.npz (the reference's int8_linear_matmul / int8_mm_dequant on CPU) through the
-    C ABI: the int8 GEMM exactly, the dequantisation within one fp16 ulp (the reference's torch kernel multiplies
-    in a different order)."""
-    from tests import _golden_check as gc
-
-    def gemm(A, B):
-        M, K = A.shape
-        N = B.shape[0]
-        a, b = torch.from_numpy(A.copy()).cuda(), torch.from_numpy(B.copy()).cuda()
-        C = torch.full((M, N), -7, device="cuda", dtype=torch.int32)
-        rc = nat.lib.cigemmlt_32(nat.lib.get_context(), N, M, K, b.data_ptr(), a.data_ptr(), C.data_ptr(), None, K, K, N,
-                                 nat.stream())
-        torch.cuda.synchronize()
-        nat.check()
-        assert rc == 0
-        return C.cpu().numpy()
-
-    def dequant(C, rs, cs, bias_bits):
-        rows, cols = C.shape
-        c = torch.from_numpy(C.copy()).cuda()
-        r, s = torch.from_numpy(rs.copy()).cuda(), torch.from_numpy(cs.copy()).cuda()
-        bias = None if bias_bits is None else nat.from_bits(bias_bits, "fp16")
-        out = torch.zeros((rows, cols), device="cuda", dtype=torch.float16)
-        nat.lib.cdequant_mm_int32_fp16(c.data_ptr(), r.data_ptr(), s.data_ptr(), out.data_ptr(), nat.ptr(bias), rows, cols,
-                                       nat.stream())
-        torch.cuda.synchronize()
-        nat.check()
-        return nat.to_bits(out)
-
-    gc.check_int8_gemm(gc.load(), gemm, dequant)

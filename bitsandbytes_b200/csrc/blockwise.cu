@@ -17,6 +17,8 @@
 //   dequant = T( mul.ftz(value(code), absmax) )                 [one rounding]
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace bnb200 {
 
 // =====================================================================================
@@ -155,6 +157,50 @@ template <> struct VecIO<__nv_bfloat16> {
     }
 };
 
+// The same codes with fewer instructions (BNB_B200_Q8_FAST=1; experimental, written at the end of round 1,
+// not yet run on a GPU).  For a sorted code book every comparison of the walk above is decided by
+// c = #{j : code[j] < x}, so the walk's end state -- its last pivot and the neighbour it may still move
+// to -- is a function of c alone: a 257-entry structural table (q8_structure) that does not depend on
+// the code values.  c comes from a 9-probe lower-bound search (3 instructions per probe instead of 8),
+// the final decision is the reference's own midpoint rule.  Equivalence with quantize_8bit is proved
+// exhaustively on the CPU for all 2^32 inputs and six code books, duplicates included
+// (tools/micro/q8_search_equiv.c).
+// entry c of the structural table, pre-scaled to byte offsets into the code book:
+// (4 * last pivot) | (4 * neighbour it may still move to) << 16
+__device__ __forceinline__ uint32_t q8_structure(int c) {
+    int pivot = 127, up = 255, lp = 0;
+#pragma unroll
+    for (int i = 64; i > 0; i >>= 1) {
+        const bool gt = pivot < c;
+        lp = gt ? pivot : lp;
+        up = gt ? up : pivot;
+        pivot += gt ? i : -i;
+    }
+    return (uint32_t)(4 * pivot) | ((uint32_t)(4 * (pivot < c ? up : lp)) << 16);
+}
+
+// all indices are kept as BYTE offsets (c4 = 4 c) so that every probe is one LDS with an immediate,
+// one FSETP and one predicated add
+__device__ __forceinline__ unsigned quantize_8bit_fast(const float* __restrict__ scode,
+                                                       const uint32_t* __restrict__ spo, float x) {
+    const char* cb = reinterpret_cast<const char*>(scode);
+    unsigned c4 = 0;
+#pragma unroll
+    for (int s = 128; s > 0; s >>= 1)
+        c4 += (*reinterpret_cast<const float*>(cb + c4 + 4 * (s - 1)) < x) ? 4u * s : 0u;
+    c4 += (c4 == 1020u && scode[255] < x) ? 4u : 0u;
+    const uint32_t po = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(spo) + c4);
+    const unsigned p4 = po & 0xffffu, o4 = po >> 16;
+    const float midpoint = mul_ftz(*reinterpret_cast<const float*>(cb + o4) + *reinterpret_cast<const float*>(cb + p4), 0.5f);
+    const bool move = (p4 < c4) ? (x > midpoint) : (x < midpoint);
+    return (move ? o4 : p4) >> 2;
+}
+
+template <int QT>
+__device__ __forceinline__ unsigned quantize_8bit_any(const float* scode, const uint32_t* spo, float x) {
+    return QT == kGeneral8bitFast ? quantize_8bit_fast(scode, spo, x) : quantize_8bit(scode, x);
+}
+
 constexpr int kQThreads = 256;
 constexpr int kQEPT = 16; // elements per thread
 
@@ -167,9 +213,15 @@ __global__ void __launch_bounds__(kQThreads)
     constexpr int V = kQEPT / VE; // vectors per thread
     __shared__ float scode[256];
     __shared__ float swarp[kQThreads / 32];
+    __shared__ uint32_t spo[QT == kGeneral8bitFast ? 257 : 1];
+    constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;
 
-    if (QT == kGeneral8bit) {
+    if (k8) {
         scode[threadIdx.x] = code[threadIdx.x];
+        if (QT == kGeneral8bitFast) {
+            spo[threadIdx.x] = q8_structure(threadIdx.x);
+            if (threadIdx.x == 0) spo[256] = q8_structure(256);
+        }
         __syncthreads();
     }
 
@@ -212,14 +264,14 @@ __global__ void __launch_bounds__(kQThreads)
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const long long e0 = blk_base + (long long)(j + v * G) * VE;
-            if (QT == kGeneral8bit) {
+            if (k8) {
                 uint32_t w[VE / 4];
 #pragma unroll
                 for (int q = 0; q < VE / 4; ++q) {
-                    uint32_t b0 = quantize_8bit(scode, mul_ftz(x[v][4 * q + 0], inv));
-                    uint32_t b1 = quantize_8bit(scode, mul_ftz(x[v][4 * q + 1], inv));
-                    uint32_t b2 = quantize_8bit(scode, mul_ftz(x[v][4 * q + 2], inv));
-                    uint32_t b3 = quantize_8bit(scode, mul_ftz(x[v][4 * q + 3], inv));
+                    uint32_t b0 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 0], inv));
+                    uint32_t b1 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 1], inv));
+                    uint32_t b2 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 2], inv));
+                    uint32_t b3 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 3], inv));
                     w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
                 }
                 if (VE == 4)
@@ -253,8 +305,14 @@ __global__ void __launch_bounds__(256)
                                       float* __restrict__ absmax, uint8_t* __restrict__ out, int bs,
                                       long long first_block, long long n) {
     __shared__ float scode[256];
-    if (QT == kGeneral8bit) {
+    __shared__ uint32_t spo[QT == kGeneral8bitFast ? 257 : 1];
+    constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;
+    if (k8) {
         scode[threadIdx.x] = code[threadIdx.x];
+        if (QT == kGeneral8bitFast) {
+            spo[threadIdx.x] = q8_structure(threadIdx.x);
+            if (threadIdx.x == 0) spo[256] = q8_structure(256);
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -270,9 +328,9 @@ __global__ void __launch_bounds__(256)
         for (int o = 16; o > 0; o >>= 1) m = max_ftz(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) absmax[b] = m;
         const float inv = rcp_approx_ftz(m);
-        if (QT == kGeneral8bit) {
+        if (k8) {
             for (long long i = lo + lane; i < hi; i += 32)
-                out[i] = (uint8_t)quantize_8bit(scode, mul_ftz(DT<T>::to_f32(A[i]), inv));
+                out[i] = (uint8_t)quantize_8bit_any<QT>(scode, spo, mul_ftz(DT<T>::to_f32(A[i]), inv));
         } else {
             // bytes [lo/2, (hi+1)/2): element past the end reads as 0.0f (reference pads with T(0))
             for (long long i = lo + 2 * lane; i < hi; i += 64) {
@@ -288,8 +346,28 @@ __global__ void __launch_bounds__(256)
 }
 
 template <typename T, int QT>
+void launch_quantize_blockwise_impl(const float* code, const T* A, float* absmax, uint8_t* out, int blocksize,
+                                    long long n, cudaStream_t stream);
+
+template <typename T, int QT>
 void launch_quantize_blockwise(const float* code, const T* A, float* absmax, uint8_t* out, int blocksize, long long n,
                                cudaStream_t stream) {
+    if (QT == kGeneral8bit) {
+        static const bool fast = [] {
+            const char* e = getenv("BNB_B200_Q8_FAST");
+            return e != nullptr && e[0] == '1';  // experimental, not yet run on a GPU: off
+        }();
+        if (fast) {
+            launch_quantize_blockwise_impl<T, kGeneral8bitFast>(code, A, absmax, out, blocksize, n, stream);
+            return;
+        }
+    }
+    launch_quantize_blockwise_impl<T, QT>(code, A, absmax, out, blocksize, n, stream);
+}
+
+template <typename T, int QT>
+void launch_quantize_blockwise_impl(const float* code, const T* A, float* absmax, uint8_t* out, int blocksize,
+                                    long long n, cudaStream_t stream) {
     if (n <= 0) return;
     const bool pow2 = blocksize > 0 && (blocksize & (blocksize - 1)) == 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);

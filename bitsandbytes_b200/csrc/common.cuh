@@ -17,6 +17,8 @@ namespace bnb200 {
 
 // csrc/common.h:3-7 of the reference: DataType_t { General8bit = 0, FP4 = 1, NF4 = 2 }
 enum QuantType : int { kGeneral8bit = 0, kFP4 = 1, kNF4 = 2 };
+// kernel-internal variant of kGeneral8bit: the same codes through the cheaper search (blockwise.cu)
+constexpr int kGeneral8bitFast = 3;
 
 constexpr int kNumSMsB200 = 148;
 

@@ -606,3 +606,49 @@ def test_fused_forward_rejects_a_mismatched_gather_buffer_before_any_launch():
                   SimpleNamespace(M=4, N=16, dtype=torch.float16)):
         with pytest.raises(ValueError, match="different output shape"):
             parallel.fused_forward(layer, x, peers)
+
+
+def test_transformers_swaps_in_our_modules_through_the_import_shim():
+    """shim/ on PYTHONPATH: Hugging Face Transformers' bitsandbytes integration (replace_with_bnb_linear,
+    BitsAndBytesConfig) sees `bitsandbytes` >= 0.46.1 and builds OUR Linear4bit / Linear8bitLt modules --
+    host logic only (meta device), so it runs without a GPU."""
+    pytest.importorskip("transformers")
+    code = r'''
+import json, torch
+from transformers.utils import is_bitsandbytes_available
+assert is_bitsandbytes_available()
+import bitsandbytes, bitsandbytes_b200
+assert bitsandbytes is bitsandbytes_b200
+from transformers import LlamaConfig, LlamaForCausalLM, BitsAndBytesConfig
+from transformers.integrations.bitsandbytes import replace_with_bnb_linear
+cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                  num_key_value_heads=2, vocab_size=512)
+out = {}
+for tag, qc in (("4bit", BitsAndBytesConfig(load_in_4bit=True, bnb_4bit_quant_type="nf4",
+                                             bnb_4bit_compute_dtype=torch.bfloat16, bnb_4bit_use_double_quant=True)),
+                ("8bit", BitsAndBytesConfig(load_in_8bit=True, llm_int8_threshold=6.0))):
+    with torch.device("meta"):
+        model = LlamaForCausalLM(cfg)
+    model = replace_with_bnb_linear(model, modules_to_not_convert=["lm_head"], quantization_config=qc)
+    mods = [(n, type(m).__module__, type(m).__name__) for n, m in model.named_modules()
+            if type(m).__name__ in ("Linear4bit", "Linear8bitLt", "Linear")]
+    q = model.model.layers[0].self_attn.q_proj
+    out[tag] = {"mods": mods, "weight": type(q.weight).__name__,
+                "detail": [q.weight.quant_type, q.weight.compress_statistics, str(q.compute_dtype)] if tag == "4bit"
+                else [float(q.state.threshold), bool(q.state.has_fp16_weights)]}
+print(json.dumps(out))
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(ROOT / "shim"), str(ROOT), os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    for tag, cls, wcls in (("4bit", "Linear4bit", "Params4bit"), ("8bit", "Linear8bitLt", "Int8Params")):
+        mods = out[tag]["mods"]
+        ours = [m for m in mods if m[2] == cls]
+        assert len(ours) == 14 and all(m[1].startswith("bitsandbytes_b200.") for m in ours)
+        assert [m[0] for m in mods if m[2] == "Linear"] == ["lm_head"]
+        assert out[tag]["weight"] == wcls
+    assert out["4bit"]["detail"] == ["nf4", True, "torch.bfloat16"]
+    assert out["8bit"]["detail"] == [6.0, False]

@@ -20,9 +20,14 @@ One JSON line on rank 0:
 
 Multi-GPU: the default workload shards by tokens (independent units, no data-path collective):
 every rank runs the same layer on its own 4096-token batch -> "scaling": "weak".
-``--workload blockwise_c1`` / ``int8_c3`` cover BASELINE configs[0] (on the GPU) and configs[2]
-(bitsandbytes_b200/bench_paths.py).  ``--workload sharded70b`` measures the column-sharded FP4+double-quant 8192 -> 28672 layer with
-an NCCL all-gather of the partial outputs (BASELINE.json configs[3]; strong scaling).
+The default line also carries
+  ref_cuda   the reference's OWN CUDA route for the headline shape on the same box (its dequantize kernel from
+             oracle/_ref/libbitsandbytes_cuda_ref.so + cuBLAS, and cuBLAS bf16 alone), measured after the timed region
+  secondary  the other BASELINE.json configs (benchmarks/paths.py): configs[1] at M in {1,16,256} and the 11008
+             shapes, configs[0] blockwise quantize/dequantize GB/s vs the HBM peak, configs[2] Linear8bitLt,
+             configs[4] the Llama-3-8B replica and -- under torchrun -- configs[3] the column-sharded 70B layer.
+``--workload blockwise_c1`` / ``int8_c3`` / ``sharded70b`` / ``llama8b`` print those as stand-alone lines.
+``--no-secondary`` skips them.
 """
 import argparse
 import json
@@ -58,6 +63,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--layers", type=int, default=32, help="llama8b workload: number of decoder layers")
     return ap.parse_args()
 
@@ -209,6 +215,82 @@ def cpu_int8_sample(x_fp16_cpu, cb_np, scb_np, M, N, K):
             "sample": f"{rows} of {M} token rows: row quantise + int8 GEMM + dequantise (outlier addmm not included)"}
 
 
+# ------------------------------------------------------------------------------------------ secondary configs
+def secondary_results(dev, args, N, K, M, qt, nested, with_cpu):
+    """(ref_cuda, secondary): the reference's CUDA route at the headline shape, and the BASELINE.json configs the
+    headline does not cover (rank 0, one GPU, after the timed region).  A failing item reports its error and
+    does not take the line down."""
+    import torch
+
+    from benchmarks import paths
+
+    ref = paths.load_ref_cuda()
+    sec = {}
+
+    def guard(name, fn):
+        try:
+            sec[name] = fn()
+        except Exception as exc:  # noqa: BLE001
+            sec[name] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
+    ref_cuda = None
+    try:
+        h = paths.measure_c2(dev, N, K, M, qt, nested, ref=ref, n_calls=40)
+        ref_cuda = {"dequant_cublas_us": (h.get("ref_cuda") or {}).get("us"), "cublas_bf16_us": h.get("cublas_bf16_us"),
+                    "ours_us": h["us"], "route": (h.get("ref_cuda") or {}).get("route"),
+                    "library": "oracle/_ref/libbitsandbytes_cuda_ref.so (built from the reference sources)" if ref else None,
+                    "timing": "CUDA-graph replay of 40 back-to-back launches over rotating buffer sets, same process"}
+    except Exception as exc:  # noqa: BLE001
+        ref_cuda = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
+
+    for (n, k, m) in ((4096, 4096, 1), (4096, 4096, 16), (4096, 4096, 256), (11008, 4096, 4096), (4096, 11008, 4096)):
+        if (n, k, m) == (N, K, M):
+            continue
+
+        def one(n=n, k=k, m=m):
+            r = paths.measure_c2(dev, n, k, m, "nf4", False, ref=ref)
+            if with_cpu and m < 4096:
+                W = (torch.randn(n, k) / k**0.5).to(torch.bfloat16)
+                import oracle
+
+                packed, absmax = oracle.quantize_blockwise(W.float().numpy().reshape(-1), 64, "nf4")
+                _, info, _, _ = cpu_reference(n, k, m, "nf4", torch.from_numpy(packed), torch.from_numpy(absmax),
+                                              torch.randn(m, k).to(torch.bfloat16), budget_s=3.0, steps=3)
+                r["cpu_baseline"] = {kk: info[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            return r
+
+        guard(f"c2_{n}x{k}_m{m}", one)
+
+    def blockwise():
+        r = paths.measure_blockwise(dev, ref)
+        if with_cpu:
+            import bitsandbytes_b200.functional as F
+
+            r["cpu_baseline"] = cpu_blockwise_sample(4 * 1024 * 1024, F.create_dynamic_map().numpy())
+        return r
+
+    guard("blockwise_c1", blockwise)
+
+    def int8():
+        r = paths.measure_int8_c3(dev)
+        cpu_args = r.pop("_cpu_args")
+        if with_cpu:
+            r["cpu_baseline"] = cpu_int8_sample(*cpu_args)
+        return r
+
+    guard("int8_c3", int8)
+
+    def llama():
+        from benchmarks.llama import measure_llama8b
+
+        return measure_llama8b(dev, 32, 64)
+
+    guard("llama8b", llama)
+    return ref_cuda, sec
+
+
 # ------------------------------------------------------------------------------------------ main
 def _protect_stdout():
     """Native libraries (NCCL's version banner, cuBLAS warnings) write to file descriptor 1; the
@@ -227,18 +309,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "sharded70b":
-        from bitsandbytes_b200.bench_sharded import run_sharded70b
+        from benchmarks.sharded import run_sharded70b
 
         return run_sharded70b(args, rank, world, local_rank)
     if args.workload in ("blockwise_c1", "int8_c3"):
-        from bitsandbytes_b200 import bench_paths
+        from benchmarks import paths as bench_paths
 
         if args.workload == "blockwise_c1":
             return bench_paths.run_blockwise_c1(args, rank, world, local_rank,
                                                 None if args.no_cpu_baseline else cpu_blockwise_sample)
         return bench_paths.run_int8_c3(args, rank, world, local_rank, None if args.no_cpu_baseline else cpu_int8_sample)
     if args.workload == "llama8b":
-        from bitsandbytes_b200.bench_e2e import run_llama8b
+        from benchmarks.llama import run_llama8b
 
         return run_llama8b(args, rank, world, local_rank)
     N, K, M, qt, nested = WORKLOADS[args.workload]
@@ -249,6 +331,8 @@ def main():
         # the reference's own CPU implementation, rank 0 only, bounded samples
         if rank != 0:
             return
+        # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core whatever the launcher
+        torch.set_num_threads(os.cpu_count() or 1)
         torch.manual_seed(0)
         W = (torch.randn(N, K) / K**0.5).to(torch.bfloat16)
         x = torch.randn(M, K).to(torch.bfloat16)
@@ -262,7 +346,10 @@ def main():
         line = {"impl": "reference", "metric": "nf4_linear4bit_forward_tflops", "value": tflops, "unit": "TFLOPS",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": args.workload, "N": N, "K": K, "M": M, "quant_type": qt, "blocksize": 64,
+                "config": {"workload": args.workload, "N": N, "K": K, "M_per_gpu": M, "global_tokens": M * args.gpus,
+                           "quant_type": qt, "blocksize": 64, "double_quant": nested,
+                           "parallelism": f"token-sharded replicas x{args.gpus} (no data-path collective)",
+                           "l2": "n/a (host run)",
                            "note": "reference CPU backend on host cores; each step is a bounded row sample"},
                 "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": tflops, "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -391,6 +478,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * flops * args.steps / (float(t.item()) * 1e-3) / 1e12
 
+    # ---------------------------------------------------------------- configs[3] under torchrun (all ranks)
+    sharded = None
+    if dist is not None and not args.no_secondary:
+        try:
+            from benchmarks.sharded import measure_sharded70b
+
+            sets = None
+            torch.cuda.empty_cache()
+            sharded = measure_sharded70b(dev, rank, world, max(10, min(args.steps, 50)), args.warmup)
+        except Exception as exc:  # noqa: BLE001
+            sharded = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -409,14 +508,17 @@ def main():
     else:
         peak, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
     achieved = flops / (kernel_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src, kernel_name = None, None, "gemm4_pair_kernel<bf16, NF4> (cta_group::2)" if M >= 512 else "gemm4_tc_kernel<bf16, NF4>"
     try:
         prof = json.loads((ROOT / "profiles" / "summary.json").read_text())
-        traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        ent = prof.get(args.workload, {})
+        traffic = ent.get("dram_bytes_per_launch")
+        traffic_src = ent.get("source")
+        kernel_name = ent.get("kernel", kernel_name)
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "gemm4_tc_kernel<bf16, NF4, MT=256>",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": kernel_ms}
 
     cpu = None
@@ -424,6 +526,15 @@ def main():
         qW, qs, x = sets[0]
         _, cpu, _, _ = cpu_reference(N, K, M, qt, qW.reshape(-1).cpu(), qs.absmax.cpu(), x.cpu(), budget_s=15.0, steps=5)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    sets = None
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- the reference's CUDA route + the other configs
+    ref_cuda, secondary = None, None
+    if not args.no_secondary:
+        ref_cuda, secondary = secondary_results(dev, args, N, K, M, qt, nested, world == 1 and not args.no_cpu_baseline)
+        if sharded is not None:
+            secondary["sharded70b"] = sharded
 
     line = {
         "metric": "nf4_linear4bit_forward_tflops", "value": value, "unit": "TFLOPS", "n_gpus": world,
@@ -439,6 +550,8 @@ def main():
         "gpu_launches": args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "ref_cuda": ref_cuda,
+        "secondary": secondary,
         "clocks": dict(clocks.summary(), window=f"timed region + {clock_extra_steps} untimed steps of the same loop"),
         "wall_s": t_wall,
     }

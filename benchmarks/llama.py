@@ -14,7 +14,7 @@ import time
 def swap_linears(model, quant_type="nf4", compress_statistics=False, skip=("lm_head",)):
     import torch
 
-    from .nn import Linear4bit, Params4bit
+    from bitsandbytes_b200.nn import Linear4bit, Params4bit
 
     n = 0
     for name, mod in list(model.named_modules()):
@@ -37,12 +37,23 @@ def swap_linears(model, quant_type="nf4", compress_statistics=False, skip=("lm_h
 
 def run_llama8b(args, rank: int, world: int, local_rank: int) -> None:
     import torch
-    from transformers import LlamaConfig, LlamaForCausalLM
 
     if rank != 0:
         return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    print(json.dumps(measure_llama8b(dev, int(getattr(args, "layers", 32) or 32), args.steps)), flush=True)
+
+
+def measure_llama8b(dev, layers: int = 32, steps: int = 64):
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    class _A:
+        pass
+
+    args = _A()
+    args.layers, args.steps = layers, steps
     # cuDNN's SDPA backend rebuilds its plan on the host for every new KV length (~12 ms per call in
     # decode); the flash / memory-efficient backends do not.  Attention is not part of the measured path.
     torch.backends.cuda.enable_cudnn_sdp(False)
@@ -141,4 +152,6 @@ def run_llama8b(args, rank: int, world: int, local_rank: int) -> None:
         "prefill_ms": prefill_ms, "prefill_tokens_per_s": prompt_len / (prefill_ms * 1e-3), "build_s": t_build,
         "published_reference": "H100 SXM, bitsandbytes 0.45: Llama 3.1 8B NF4 bs=1 30.14 tok/s (benchmarking/README.md:91)",
     }
-    print(json.dumps(line), flush=True)
+    del model
+    torch.cuda.empty_cache()
+    return line

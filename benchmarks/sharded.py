@@ -20,13 +20,30 @@ def run_sharded70b(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from . import functional as F
-    from .parallel import ColumnParallelLinear4bit, PeerGather, fused_forward, slice_quantized_weight
-
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    line = measure_sharded70b(dev, rank, world, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_sharded70b(dev, rank: int, world: int, steps: int, warmup: int):
+    """All ranks call this (the process group is the caller's); returns the result line (meaningful on rank 0)."""
+    import torch
+    import torch.distributed as dist
+
+    import bitsandbytes_b200.functional as F
+    from bitsandbytes_b200.parallel import ColumnParallelLinear4bit, PeerGather, fused_forward, slice_quantized_weight
+
+    class _A:
+        pass
+
+    args = _A()
+    args.steps, args.warmup = steps, warmup
     M = 4096
     torch.manual_seed(0)  # identical weight on every rank: quantise once "globally", then slice
     W = (torch.randn(N_FULL, K_FULL, device=dev) / K_FULL**0.5).to(torch.bfloat16)
@@ -87,7 +104,7 @@ def run_sharded70b(args, rank: int, world: int, local_rank: int) -> None:
             fused_note = repr(exc)[:300]
     wall = time.perf_counter() - t0
     ms_value = ms_fused if ms_fused is not None else ms_all
-    if rank == 0:
+    if True:
         line = {
             "metric": "fp4_dq_column_sharded_linear_tflops", "value": flops * args.steps / (ms_value * 1e-3) / 1e12,
             "unit": "TFLOPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -106,6 +123,6 @@ def run_sharded70b(args, rank: int, world: int, local_rank: int) -> None:
             "gather_bytes_per_rank": 2 * M * shard.rows * (world - 1),
             "gpu_launches": args.steps, "wall_s": wall,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del layer, shard, qW, qs, xs, stage
+    torch.cuda.empty_cache()
+    return line

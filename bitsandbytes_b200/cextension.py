@@ -60,6 +60,9 @@ def _signatures():
     sig["cbnb_b200_gemm_4bit_force_path"] = ([_I32], None)
     # (A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc, blocksize, quant_type, dtype, stream)
     sig["cbnb_b200_gemm_4bit_strided"] = ([_VOIDP] * 8 + [_I32] * 7 + [_VOIDP], None)
+    # (A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc, blocksize, quant_type, dtype,
+    #  mt, force_splits, trace, stream) -> int
+    sig["cbnb_b200_gemm_4bit_pair"] = ([_VOIDP] * 8 + [_I32] * 9 + [_VOIDP, _VOIDP], _I32)
     sig["cbnb_b200_gemm_4bit_multi_out"] = ([_VOIDP] * 7 + [_I32] + [_VOIDP] + [_I32] * 7 + [_VOIDP], _I32)
     # (CA, CB, SCA, SCB, bias, out, M, N, K, dtype, stream) -> int
     sig["cbnb_b200_int8_scaled_mm"] = ([_VOIDP] * 6 + [_I32] * 4 + [_VOIDP], _I32)

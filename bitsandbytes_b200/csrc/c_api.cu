@@ -36,6 +36,11 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
                      const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
                      int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers = nullptr,
                      int n_peers = 0);
+template <typename T>
+bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                       const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
+                       int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers, int n_peers,
+                       int mt_override, int force_splits, long long* trace);
 void launch_int8_vector_quant(const void* A, int8_t* out, float* rowStats, int* col_flags, float threshold, int rows,
                               int cols, int dtype, cudaStream_t stream);
 void launch_dequant_mm_int32_fp16(const int* A, const float* rowStats, const float* colStats, __half* out,
@@ -325,6 +330,27 @@ int cbnb_b200_gemm_4bit_multi_out(const void* A, const uint8_t* B, const float* 
         ok = launch_gemm4_tc<__nv_bfloat16>((const __nv_bfloat16*)A, B, absmax, absmax_8bit, absmax_code,
                                             absmax_offset, (__nv_bfloat16*)outs[0], (const __nv_bfloat16*)bias, M, N, K,
                                             ldc, blocksize, quant_type, stream, outs + 1, n_outs - 1);
+    return ok ? 0 : 100;
+}
+
+// Developer / test entry: the CTA-pair kernel of gemm4_pair.cu with an explicit token tile (mt = 128 | 256 |
+// 384, 0 = automatic), a forced K split (0 = the production rule, s = every tile split s ways, 100 + s = only
+// the partial last wave) and an optional event trace (device buffer of 2 * 10 * 256 int64 clock values of
+// cluster 0; NULL = the production build).  Returns 0, or 100 when the shape is not served by that kernel.
+int cbnb_b200_gemm_4bit_pair(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                             const float* absmax_code, const float* absmax_offset, void* out, const void* bias, int M,
+                             int N, int K, int ldc, int blocksize, int quant_type, int dtype, int mt, int force_splits,
+                             long long* trace, cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return 0;
+    bool ok = false;
+    if (dtype == 1)
+        ok = launch_gemm4_pair<__half>((const __half*)A, B, absmax, absmax_8bit, absmax_code, absmax_offset,
+                                       (__half*)out, (const __half*)bias, M, N, K, ldc, blocksize, quant_type, stream,
+                                       nullptr, 0, mt, force_splits, trace);
+    else if (dtype == 2)
+        ok = launch_gemm4_pair<__nv_bfloat16>((const __nv_bfloat16*)A, B, absmax, absmax_8bit, absmax_code,
+                                              absmax_offset, (__nv_bfloat16*)out, (const __nv_bfloat16*)bias, M, N, K,
+                                              ldc, blocksize, quant_type, stream, nullptr, 0, mt, force_splits, trace);
     return ok ? 0 : 100;
 }
 

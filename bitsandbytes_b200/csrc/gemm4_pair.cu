@@ -1,0 +1,667 @@
+// gemm4_pair.cu -- NF4/FP4 dequant-fused GEMM for LARGE token counts: a CTA PAIR (cta_group::2) per
+// 256-feature x MT-token output tile, decoded weights through tensor memory.
+//
+// Same contract and numerics as gemm4_tc.cu (reference _ops.py:239-295, gemm_4bit_mma.cuh:99-101;
+// on B200 the reference itself takes dequantize + cuBLAS for these shapes, backends/cuda/ops.py:617-623,
+// 904-916):   out[m, n] = T( sum_k X[m, k] * rn_T(value(code[n, k]) * scale[n, k / bs])  + bias[n] ).
+//
+// Why a second kernel.  The one-CTA kernel of gemm4_tc.cu is bound by what an SM can pull out of L2
+// (round 1: 72 KB per 1024 MMA cycles = 70 B/clk against the ~45 B/clk/SM the L2 sustains chip-wide).
+// Here the two CTAs of a cluster own adjacent 128-feature halves of one 256-feature tile and ONE
+// tcgen05.mma.cta_group::2 drives both SMs' tensor cores (UMMA M = 256); the activation tile is split
+// between the two shared memories, so each SM ingests HALF the activation bytes.  The pipeline is
+// rebuilt around that:
+//   * a-stage = 64 k-elements = 32 TMEM columns of decoded weights per CTA.  The ring of a-stages (TMEM
+//     A slots + the matching activation slots in shared memory) has one `full` barrier per stage on the
+//     LEADER (TMA bytes of both CTAs + its own decode warps + one relayed arrival for the peer's) and one
+//     `empty` barrier per stage in each CTA (tcgen05.commit multicast).
+//   * packed codes travel in their OWN, deeper ring (128 k-elements = 8 KB per stage, 8 stages) fed by a
+//     separate producer thread, so the decode warps run ahead of the tensor core instead of starting a
+//     stage's decode only after the MMA that frees the matching TMEM slot has retired.
+//   * 16 decode warps = 4 groups x 4 warps (one per TMEM lane quarter); group g decodes the a-stages
+//     i = g (mod 4): a thread owns one feature row and the 64 codes of the stage (= one quantisation block at
+//     the default block size, so the 16-entry table is built once per 64 weights), PRMT-decodes them in
+//     registers (decode4.cuh) and writes them with ONE tcgen05.st.32x32b.x32.
+//   * MT = 384 tokens per tile (two N = 192 MMAs per k-step, 384 accumulator columns + 4 x 32 weight
+//     columns = the whole 512-column TMEM): a decoded weight feeds 384 MACs instead of 256, which takes
+//     the ALU pipe (the PRMT decode: ~2.9 ALU instructions per weight, 64 lanes/clk/SM) off the critical
+//     path.  MT = 256 (one N = 256 MMA, 8 stages) serves smaller token counts.
+//   * the partial last wave is split along K (2..4 ways); the splits of a tile exchange fp32 partials
+//     through an L2-resident workspace and the LAST ARRIVER (atomic counter, no spinning) sums them in
+//     split order -- deterministic, and safe under any co-scheduling.
+//
+// Warp roles (608 threads): warp 0 activation producer (TMA), warp 1 MMA issuer (leader) / relay (peer)
+// + TMEM allocator, warps 2..17 decode then epilogue, warp 18 code producer (TMA).
+#include "common.cuh"
+#include "decode4.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace bnb200 {
+
+// shared with gemm4_tc.cu (split-K scratch per (device, stream))
+struct Gemm4Workspace {
+    float* partial;
+    int* counters;
+};
+bool gemm4_get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_counters, Gemm4Workspace* out);
+
+namespace {
+
+constexpr int kTileN = 128;        // features per CTA (TMEM lanes); the pair owns 256
+constexpr int kAK = 64;            // a-stage: k-elements per TMEM A slot (32 columns)
+constexpr int kCK = 128;           // code stage: k-elements per TMA box of packed codes (64 B per row)
+constexpr int kCodeStageBytes = kTileN * (kCK / 2);  // 8 KB
+constexpr int kNC = 8;             // code ring depth
+constexpr int kDecodeWarps = 16;   // 4 groups x 4 warps
+constexpr int kThreads = 32 * (2 + kDecodeWarps + 1);
+constexpr int kScaleDepth = 4;     // per-thread register ring of scales (stages of one group)
+constexpr int kTraceStages = 256;  // TRACE builds: events are kept for the first 256 a-stages of cluster 0
+constexpr int kTraceRoles = 10;
+
+struct PairParams {
+    const uint8_t* B;
+    const float* absmax;
+    const uint8_t* absmax_8bit;
+    const float* absmax_code;
+    const float* absmax_offset;
+    const void* bias;
+    void* out;
+    void* peer_out[7];
+    int n_peers;
+    float* ws_partial;   // [split slots][MT columns][128 rows] fp32
+    int* ws_counter;     // one per split (tile, CTA rank); zero on entry, reset by the last arriver
+    long long* trace;    // TRACE builds only
+    int M, N, K, ldc;
+    int log2_bs;
+    int ka_total;        // a-stages in K
+    int n_pairs;         // 256-feature tiles along N
+    int tiles_total;
+    int tiles_main;      // tiles [0, tiles_main) are computed by one cluster each, the rest by `splits_tail`
+    int splits_tail;
+};
+
+template <typename T> struct TcFmt;
+template <> struct TcFmt<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
+template <> struct TcFmt<__half> { static constexpr uint32_t kFmt = 0; };
+
+template <int MT> struct PairCfg {
+    static_assert(MT == 128 || MT == 256 || MT == 384, "token tile");
+    static constexpr int kNSub = MT == 384 ? 2 : 1;          // MMAs per k-step
+    static constexpr int kUmmaN = MT / kNSub;                // 128 / 256 / 192
+    static constexpr int kBoxRows = kUmmaN / 2;              // token rows this CTA stages per MMA
+    static constexpr int kSubBytes = kBoxRows * 128;         // one [kBoxRows x 64] bf16 box, 128-byte swizzle
+    static constexpr int kXStageBytes = kNSub * kSubBytes;   // MT/2 tokens x 128 B
+    static constexpr int kNA = (512 - MT) / 32 > 8 ? 8 : (512 - MT) / 32;  // a-stage ring depth: 4 (MT=384) or 8
+    static constexpr uint32_t kACol0 = MT;                   // D: [0, MT); A slot s: MT + 32 s
+    static constexpr size_t kSmemBytes = 1024 + size_t(kNA) * kXStageBytes + size_t(kNC) * kCodeStageBytes + 512;
+    static_assert(kSubBytes % 1024 == 0, "128-byte swizzle atoms");
+};
+
+template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams& p, int role, int i) {
+    if constexpr (TRACE) {
+        if (p.trace != nullptr && blockIdx.x < 2 && i < kTraceStages)
+            p.trace[((long long)blockIdx.x * kTraceRoles + role) * kTraceStages + i] = clock64();
+    }
+}
+
+template <typename T, int QT, int MT, bool TRACE>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm4_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const PairParams p) {
+    using Cfg = PairCfg<MT>;
+    constexpr int kNA = Cfg::kNA;
+    constexpr int kXStageBytes = Cfg::kXStageBytes;
+    constexpr uint32_t kACol0 = Cfg::kACol0;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sx = smem;                                   // [kNA][kNSub][kBoxRows x 128 B]
+    uint8_t* sw = smem + kNA * kXStageBytes;              // [kNC][128 x 64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sw + kNC * kCodeStageBytes);
+    uint64_t* full = bars;                  // [kNA]
+    uint64_t* empty = bars + kNA;           // [kNA]
+    uint64_t* c_full = bars + 2 * kNA;      // [kNC]
+    uint64_t* c_empty = c_full + kNC;       // [kNC]
+    uint64_t* acc_full = c_empty + kNC;     // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = ptx::cluster_ctarank();
+    const bool leader = cta_rank == 0;
+
+    // cluster -> (tile, K split)
+    const int cid = blockIdx.x >> 1;
+    int tile, split = 0, splits = 1;
+    if (cid < p.tiles_main) {
+        tile = cid;
+    } else {
+        const int r = cid - p.tiles_main;
+        splits = p.splits_tail;
+        tile = p.tiles_main + r / splits;
+        split = r - (r / splits) * splits;
+    }
+    const int n0 = (tile % p.n_pairs) * (2 * kTileN) + (int)cta_rank * kTileN;  // this CTA's 128 features
+    const int m0 = (tile / p.n_pairs) * MT;
+    // K range of this split, in a-stages; boundaries on even a-stages (= whole code stages)
+    int per = (p.ka_total + splits - 1) / splits;
+    per += per & 1;
+    const int st_begin = split * per;
+    int st_end = st_begin + per;
+    if (st_end > p.ka_total) st_end = p.ka_total;
+    const int nst = st_end - st_begin;  // >= 1: the host only splits when every split gets work
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int s = 0; s < kNA; ++s) {
+            // leader: producer's expect_tx arrival + 4 decode warps + the peer's relayed arrival
+            // peer:   its 4 decode warps (the relay warp waits on it)
+            ptx::mbar_init(&full[s], leader ? 6 : 4);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < kNC; ++s) {
+            ptx::mbar_init(&c_full[s], 1);
+            ptx::mbar_init(&c_empty[s], 8);  // the 2 x 4 decode warps that read a code stage
+        }
+        ptx::mbar_init(acc_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_pair<512>(tmem_slot);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================== activation producer
+        if (lane == 0) {
+            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nst; ++i) {
+                ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, i);
+                trace_ev<TRACE>(p, 0, i);
+                const int k0 = (st_begin + i) * kAK;
+                if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * kXStageBytes);
+                uint8_t* dst = sx + s * kXStageBytes;
+#pragma unroll
+                for (int sub = 0; sub < Cfg::kNSub; ++sub)
+                    ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_full0 + 8u * s, k0,
+                                          m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
+                if (++s == kNA) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 18) {
+        // ================================================================== code producer
+        if (lane == 0) {
+            const int ncs = (nst + 1) >> 1;
+            int cs = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < ncs; ++j) {
+                ptx::mbar_wait_bounded(&c_empty[cs], ph ^ 1u, 2, j);
+                ptx::mbar_arrive_expect_tx(&c_full[cs], kCodeStageBytes);
+                // bytes [k/2, k/2 + 64) of rows n0 .. n0+127 (rows past N / bytes past K/2: zero-filled)
+                ptx::tma_load_2d(sw + cs * kCodeStageBytes, &tmap_w, &c_full[cs], ((st_begin + 2 * j) * kAK) / 2, n0);
+                if (++cs == kNC) {
+                    cs = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0;
+        uint32_t ph = 0;
+        if (!leader) {
+            // ============================================================== relay (peer CTA)
+            // "my decode group has filled A slot s": ONE cluster-scope arrive per stage on the leader's barrier
+            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+            for (int i = 0; i < nst; ++i) {
+                ptx::mbar_wait_bounded(&full[s], ph, 3, i);
+                if (lane == 0) {
+                    ptx::mbar_arrive_cluster(lead_full0 + 8u * s);
+                    trace_ev<TRACE>(p, 7, i);
+                }
+                __syncwarp();
+                if (++s == kNA) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        } else {
+            // ============================================================== MMA issuer (leader CTA)
+            constexpr uint32_t idesc =
+                ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
+            for (int i = 0; i < nst; ++i) {
+                ptx::mbar_wait_bounded(&full[s], ph, 4, i);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    trace_ev<TRACE>(p, 1, i);
+                    const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
+                    const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
+#pragma unroll
+                    for (int k = 0; k < kAK / 16; ++k) {
+#pragma unroll
+                        for (int sub = 0; sub < Cfg::kNSub; ++sub) {
+                            // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
+                            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xs + sub * Cfg::kSubBytes) + 2 * k;
+                            ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
+                                                 (i | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::tc_commit_pair(&empty[s], 0x3);
+                    if (i == nst - 1) ptx::tc_commit_pair(acc_full, 0x3);
+                    trace_ev<TRACE>(p, 2, i);
+                }
+                __syncwarp();
+                if (++s == kNA) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ================================================================== decode warps
+        const int dw = warp - 2;        // 0..15
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may touch
+        const int grp = dw >> 2;        // decodes the a-stages i with i % 4 == grp
+        const int row = quarter * 32 + lane;
+        const int n = n0 + row;
+        const bool n_ok = n < p.N;
+        const long long e_row = (long long)(n_ok ? n : 0) * p.K;
+        ScaleSrc sc{p.absmax, p.absmax_8bit, p.absmax_code, p.absmax_offset ? __ldg(p.absmax_offset) : 0.0f};
+        const bool two_scales = p.log2_bs == 5;
+        const uint32_t sw_row = (uint32_t)row * 64u;
+        const uint32_t sw_x = (uint32_t)((row >> 1) & 3);  // 64-byte swizzle: chunk c of row r sits at c ^ ((r>>1)&3)
+        const bool tracer = TRACE && quarter == 0 && lane == 0;
+
+        float wsc[kScaleDepth][2];
+        auto fetch = [&](int j, int t) {
+            wsc[j][0] = wsc[j][1] = 0.f;
+            const int i = 4 * t + grp;
+            if (i < nst && n_ok) {
+                const long long e = e_row + (long long)(st_begin + i) * kAK;
+                wsc[j][0] = sc.load(e >> p.log2_bs);
+                if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < kScaleDepth; ++j) fetch(j, j);
+
+        const int cnt = (nst - grp + 3) >> 2;  // a-stages this group owns
+        for (int t0 = 0; t0 < cnt; t0 += kScaleDepth) {
+#pragma unroll
+            for (int j = 0; j < kScaleDepth; ++j) {
+                const int t = t0 + j;
+                if (t < cnt) {
+                    const int i = 4 * t + grp;
+                    const int s = i % kNA;
+                    const uint32_t ph = (uint32_t)(i / kNA) & 1u;
+                    const int cj = i >> 1;
+                    const int cs = cj % kNC;
+                    const uint32_t cph = (uint32_t)(cj / kNC) & 1u;
+                    const uint32_t hsel = (uint32_t)(i & 1) * 2u;  // which 32 bytes of the 64-byte code row
+                    const float sc0 = wsc[j][0], sc1 = wsc[j][1];
+                    fetch(j, t + kScaleDepth);
+
+                    ptx::mbar_wait_bounded(&c_full[cs], cph, 5, i);
+                    if (tracer) trace_ev<TRACE>(p, 3, i);
+                    const uint8_t* wt = sw + cs * kCodeStageBytes + sw_row;
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(wt + ((hsel ^ sw_x) << 4));
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(wt + (((hsel + 1u) ^ sw_x) << 4));
+
+                    uint32_t r[32];
+                    DecodeTable tab;
+                    build_table<T, QT>(sc0, tab);
+                    decode_word(q0.x, tab, r + 0);
+                    decode_word(q0.y, tab, r + 4);
+                    decode_word(q0.z, tab, r + 8);
+                    decode_word(q0.w, tab, r + 12);
+                    if (two_scales) build_table<T, QT>(sc1, tab);
+                    decode_word(q1.x, tab, r + 16);
+                    decode_word(q1.y, tab, r + 20);
+                    decode_word(q1.z, tab, r + 24);
+                    decode_word(q1.w, tab, r + 28);
+                    // the codes are in registers (the decode consumed them): hand the code stage back
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);
+                    if (tracer) trace_ev<TRACE>(p, 4, i);
+
+                    ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 6, i);
+                    if (tracer) trace_ev<TRACE>(p, 5, i);
+                    ptx::tc_fence_after();
+                    ptx::tmem_st_x32(tmem_base + (uint32_t(quarter * 32) << 16) + kACol0 + s * 32, r);
+                    ptx::tmem_wait_st();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&full[s]);
+                    if (tracer) trace_ev<TRACE>(p, 6, i);
+                }
+            }
+        }
+
+        // ================================================================== epilogue
+        ptx::mbar_wait_bounded(acc_full, 0, 7);
+        ptx::tc_fence_after();
+        if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0);
+
+        // this warp: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4)
+        constexpr int kColsPerWarp = MT / 4;  // 32, 64 or 96
+        const int col0 = grp * kColsPerWarp;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+        T* outp = reinterpret_cast<T*>(p.out);
+        float bias_v = 0.f;
+        if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
+
+        if (splits == 1) {
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int m = m0 + col0 + c + t;
+                    if (n_ok && m < p.M) {
+                        const T val = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
+                        const long long idx = (long long)m * p.ldc + n;
+                        outp[idx] = val;
+                        for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                    }
+                }
+            }
+        } else {
+            // ---- split K: publish the fp32 partial tile ([column][row]: coalesced both ways), count in on the
+            // (tile, CTA) counter; the LAST split to arrive sums all partials in split order.  No CTA waits
+            // for another one.
+            const int tt = (tile - p.tiles_main) * 2 + (int)cta_rank;
+            float* ws_tile = p.ws_partial + (long long)tt * splits * (kTileN * MT);
+            float* my = ws_tile + (long long)split * (kTileN * MT);
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) __stcg(my + (col0 + c + t) * kTileN + row, __uint_as_float(v[t]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const int old = atomicAdd(p.ws_counter + tt, 1);
+                *s_flag = old;
+                if (old == splits - 1) p.ws_counter[tt] = 0;  // everyone has arrived: reset for the next launch
+                __threadfence();
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (*s_flag == splits - 1) {
+                for (int c = 0; c < kColsPerWarp; ++c) {
+                    const int m = m0 + col0 + c;
+                    if (m >= p.M) break;
+                    float acc = 0.f;
+                    for (int sp = 0; sp < splits; ++sp)
+                        acc += __ldcg(ws_tile + ((long long)sp * MT + col0 + c) * kTileN + row);
+                    if (n_ok) {
+                        const T val = DT<T>::from_f32(acc + bias_v);
+                        const long long idx = (long long)m * p.ldc + n;
+                        outp[idx] = val;
+                        for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                    }
+                }
+            }
+        }
+        if (tracer && grp == 0) trace_ev<TRACE>(p, 9, 0);
+    }
+
+    // ------------------------------------------------------------------ teardown
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // no CTA may exit while its peer can still arrive on / commit into its shared memory
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+// Tensor maps are pure functions of (base, shape, box): a small per-process cache keeps
+// cuTensorMapEncodeTiled (a driver call) off the per-call host path.
+struct TmapKey {
+    const void* base;
+    uint64_t rows, cols, stride;
+    uint32_t box_rows, box_cols;
+    int elem, swz;
+};
+struct TmapEntry {
+    TmapKey key;
+    CUtensorMap map;
+    bool used;
+};
+constexpr int kTmapCache = 32;
+TmapEntry g_tmaps[kTmapCache];
+int g_tmap_next = 0;
+std::mutex g_tmap_mu;
+
+bool cached_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle, uint64_t rows, uint64_t cols,
+                 uint64_t stride, uint32_t box_rows, uint32_t box_cols) {
+    const TmapKey k{base, rows, cols, stride, box_rows, box_cols, elem_bytes, swizzle};
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    for (int i = 0; i < kTmapCache; ++i) {
+        const TmapEntry& e = g_tmaps[i];
+        if (e.used && e.key.base == k.base && e.key.rows == k.rows && e.key.cols == k.cols && e.key.stride == k.stride &&
+            e.key.box_rows == k.box_rows && e.key.box_cols == k.box_cols && e.key.elem == k.elem && e.key.swz == k.swz) {
+            *out = e.map;
+            return true;
+        }
+    }
+    if (!encode_tmap_2d(out, base, elem_bytes, swizzle, rows, cols, stride, box_rows, box_cols)) return false;
+    TmapEntry& e = g_tmaps[g_tmap_next];
+    g_tmap_next = (g_tmap_next + 1) % kTmapCache;
+    e.key = k;
+    e.map = *out;
+    e.used = true;
+    return true;
+}
+
+template <typename T, int QT, int MT, bool TRACE>
+bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_splits) {
+    using Cfg = PairCfg<MT>;
+    auto kern = gemm4_pair_kernel<T, QT, MT, TRACE>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};  // the opt-in is per device
+    static int pairs_per_wave[64] = {};
+    if (dev < 0 || dev >= 64) return false;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess) {
+            set_last_error("gemm4_pair smem attr", cudaGetLastError());
+            return false;
+        }
+        attr_set[dev] = true;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    if (pairs_per_wave[dev] == 0) {
+        cudaLaunchConfig_t qc{};
+        qc.gridDim = dim3(2 * 128, 1, 1);
+        qc.blockDim = dim3(kThreads);
+        qc.dynamicSmemBytes = Cfg::kSmemBytes;
+        qc.attrs = attr;
+        qc.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &qc) == cudaSuccess && nclusters > 0) {
+            pairs_per_wave[dev] = nclusters;
+        } else {
+            (void)cudaGetLastError();
+            pairs_per_wave[dev] = device_sm_count() / 2;
+        }
+    }
+    const int P = pairs_per_wave[dev];
+
+    CUtensorMap tmap_x, tmap_w;
+    if (!cached_tmap(&tmap_x, A, 2, 128, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)Cfg::kBoxRows, 64u))
+        return false;
+    if (!cached_tmap(&tmap_w, p.B, 1, 64, (uint64_t)p.N, (uint64_t)p.K / 2, (uint64_t)p.K / 2, (uint32_t)kTileN, 64u))
+        return false;
+
+    p.n_pairs = (p.N + 2 * kTileN - 1) / (2 * kTileN);
+    const int m_tiles = (p.M + MT - 1) / MT;
+    const int tiles = p.n_pairs * m_tiles;
+    p.tiles_total = tiles;
+
+    // K split of the partial last wave (or of everything when the grid is less than half a wave)
+    int splits = 1, tiles_main = tiles;
+    const int rem = tiles % P;
+    // production: >= 8 a-stages (512 k) per split; forced (tests): >= 2
+    const int min_stages = force_splits > 0 ? 2 : 8;
+    const int max_by_k = p.ka_total / min_stages > 0 ? p.ka_total / min_stages : 1;
+    auto clamp = [&](int v) {
+        if (v > 4) v = 4;
+        if (v > max_by_k) v = max_by_k;
+        if (v < 1) v = 1;
+        // no empty split: per = ceil(ka/v) rounded up to even
+        while (v > 1) {
+            int per = (p.ka_total + v - 1) / v;
+            per += per & 1;
+            if (per * (v - 1) < p.ka_total) break;
+            --v;
+        }
+        return v;
+    };
+    if (force_splits > 0) {
+        splits = clamp(force_splits);
+        tiles_main = splits > 1 ? 0 : tiles;
+        if (force_splits >= 100) {  // 100 + s: split only the partial last wave (the production rule), s ways
+            splits = clamp(force_splits - 100);
+            tiles_main = splits > 1 ? tiles - rem : tiles;
+        }
+    } else if (rem > 0 && rem * 2 <= P) {
+        splits = clamp(P / rem);
+        tiles_main = splits > 1 ? tiles - rem : tiles;
+    }
+    p.tiles_main = tiles_main;
+    p.splits_tail = splits;
+    p.ws_partial = nullptr;
+    p.ws_counter = nullptr;
+    const int split_tiles = tiles - tiles_main;
+    if (split_tiles > 0) {
+        Gemm4Workspace ws{};
+        if (!gemm4_get_workspace(stream, size_t(split_tiles) * 2 * splits * kTileN * MT * sizeof(float),
+                                 size_t(split_tiles) * 2, &ws)) {
+            set_last_error_msg("gemm4_pair: could not allocate the split-K workspace");
+            return false;
+        }
+        p.ws_partial = ws.partial;
+        p.ws_counter = ws.counters;
+    }
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (tiles_main + split_tiles * splits), 1, 1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_x, tmap_w, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_last_error("gemm4_pair launch", e);
+        return false;
+    }
+    return true;
+}
+
+} // namespace
+
+// Large-M route of the 4-bit GEMM.  Returns false when the shape is not served here (the caller falls back
+// to the one-CTA kernel of gemm4_tc.cu).  `mt_override` (0 = automatic) and `force_splits` are for the
+// probes / tests; `trace` (device buffer of 2 * kTraceRoles * kTraceStages int64) selects the traced build.
+template <typename T>
+bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                       const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
+                       int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers, int n_peers,
+                       int mt_override, int force_splits, long long* trace) {
+    if (K < 128 || (K % 64) != 0) return false;
+    if (blocksize < 32 || (blocksize & (blocksize - 1)) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(B) & 15) != 0) return false;
+    if (quant_type != kNF4 && quant_type != kFP4) return false;
+    if (n_peers < 0 || n_peers > 7) return false;
+
+    int MT = mt_override;
+    if (MT == 0) {
+        if (M < 512) return false;  // the one-CTA kernel (with its split-K) serves the small token counts
+        // Pick the token tile by the modelled time: rounds x (cycles per a-stage) (+ the non-overlapped
+        // epilogue); MT=384 is MMA-bound (768 cycles per a-stage), MT=256 pays the decode (~ 600).
+        const int n_pairs = (N + 255) / 256;
+        const int P = device_sm_count() / 2;
+        auto cost = [&](int mt, double stage_cycles) {
+            const int tiles = n_pairs * ((M + mt - 1) / mt);
+            const int rem = tiles % P;
+            double rounds = tiles / P;
+            if (rem > 0) rounds += (rem * 2 <= P) ? 1.0 / (P / rem > 4 ? 4 : P / rem) + 0.08 : 1.0;
+            return rounds * ((K / 64) * stage_cycles + 3000.0 + 8.0 * mt);
+        };
+        MT = cost(384, 800.0) <= cost(256, 620.0) ? 384 : 256;
+    }
+    if (MT != 128 && MT != 256 && MT != 384) return false;
+
+    PairParams p{};
+    p.B = B;
+    p.absmax = absmax;
+    p.absmax_8bit = absmax_8bit;
+    p.absmax_code = absmax_code;
+    p.absmax_offset = absmax_offset;
+    p.bias = bias;
+    p.out = out;
+    p.n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) p.peer_out[r] = peers[r];
+    p.trace = trace;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.ldc = ldc;
+    p.log2_bs = ilog2_pow2(blocksize);
+    p.ka_total = K / kAK;
+
+#define BNB200_PAIR_MT(QT, TR)                                                                                         \
+    switch (MT) {                                                                                                      \
+    case 128: return launch_pair_mt<T, QT, 128, TR>(A, p, stream, force_splits);                                       \
+    case 256: return launch_pair_mt<T, QT, 256, TR>(A, p, stream, force_splits);                                       \
+    default: return launch_pair_mt<T, QT, 384, TR>(A, p, stream, force_splits);                                        \
+    }
+    if (trace != nullptr) {
+        if (quant_type == kNF4) {
+            BNB200_PAIR_MT(kNF4, true)
+        } else {
+            BNB200_PAIR_MT(kFP4, true)
+        }
+    }
+    if (quant_type == kNF4) {
+        BNB200_PAIR_MT(kNF4, false)
+    } else {
+        BNB200_PAIR_MT(kFP4, false)
+    }
+#undef BNB200_PAIR_MT
+}
+
+template bool launch_gemm4_pair<__nv_bfloat16>(const __nv_bfloat16*, const uint8_t*, const float*, const uint8_t*,
+                                               const float*, const float*, __nv_bfloat16*, const __nv_bfloat16*, int,
+                                               int, int, int, int, int, cudaStream_t, void* const*, int, int, int,
+                                               long long*);
+template bool launch_gemm4_pair<__half>(const __half*, const uint8_t*, const float*, const uint8_t*, const float*,
+                                        const float*, __half*, const __half*, int, int, int, int, int, int,
+                                        cudaStream_t, void* const*, int, int, int, long long*);
+
+} // namespace bnb200

@@ -826,69 +826,78 @@ struct Workspace {
     size_t n_counters = 0;
 };
 
+// Split-K scratch: one FIXED-SIZE block per (device, stream), so that launches on different streams never
+// share partials or counters and the launch path never reallocates.  32 MB covers every split this
+// library launches (one-CTA kernel: <= one wave of 128 x 256 fp32 tiles = 19 MB; pair kernel: <= 148 split
+// CTAs x 128 x 384 fp32 = 29 MB).  The only allocation happens on the first split-K call of a stream; it is
+// made capture-safe (relaxed capture mode around cudaMalloc) so that a CUDA-graph capture whose first
+// split-K GEMM is inside the capture still works.  The registry evicts its least recently used entry.
+constexpr size_t kWsBytes = size_t(32) << 20;
+constexpr size_t kWsCounters = 8192;
 constexpr int kMaxWs = 64;
 struct WsEntry {
     int device;
     cudaStream_t stream;
     Workspace ws;
     bool used;
+    unsigned long long stamp;
 };
 WsEntry g_ws[kMaxWs];
+unsigned long long g_ws_clock = 0;
 std::mutex g_ws_mu;  // the registry is shared by every host thread that launches GEMMs
 
-// Split-K scratch, one per (device, stream) so that launches on different streams never
-// share partials or counters.  Grown with plain cudaMalloc on first use / growth only.
 Workspace* get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_counters) {
+    if (partial_bytes > kWsBytes || n_counters > kWsCounters) return nullptr;
     std::lock_guard<std::mutex> lk(g_ws_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     WsEntry* e = nullptr;
+    WsEntry* lru = &g_ws[0];
     for (int i = 0; i < kMaxWs; ++i) {
         if (g_ws[i].used && g_ws[i].device == dev && g_ws[i].stream == stream) {
             e = &g_ws[i];
             break;
         }
-    }
-    if (e == nullptr) {
-        for (int i = 0; i < kMaxWs; ++i) {
-            if (!g_ws[i].used) {
-                e = &g_ws[i];
-                e->used = true;
-                e->device = dev;
-                e->stream = stream;
-                e->ws = Workspace{};
-                break;
-            }
+        if (!g_ws[i].used) {
+            if (lru->used) lru = &g_ws[i];
+        } else if (lru->used && g_ws[i].stamp < lru->stamp) {
+            lru = &g_ws[i];
         }
     }
-    if (e == nullptr) return nullptr;
-    if (e->ws.bytes < partial_bytes) {
-        if (e->ws.ptr) {
-            cudaStreamSynchronize(stream);
-            cudaFree(e->ws.ptr);
-        }
-        size_t want = partial_bytes < (size_t(8) << 20) ? (size_t(8) << 20) : partial_bytes;
-        if (cudaMalloc(&e->ws.ptr, want) != cudaSuccess) {
-            e->ws.ptr = nullptr;
-            e->ws.bytes = 0;
-            return nullptr;
-        }
-        e->ws.bytes = want;
+    if (e != nullptr) {
+        e->stamp = ++g_ws_clock;
+        return &e->ws;
     }
-    if (e->ws.n_counters < n_counters) {
-        if (e->ws.counters) {
-            cudaStreamSynchronize(stream);
-            cudaFree(e->ws.counters);
-        }
-        size_t want = n_counters < 4096 ? 4096 : n_counters;
-        if (cudaMalloc(&e->ws.counters, want * sizeof(int)) != cudaSuccess) {
-            e->ws.counters = nullptr;
-            e->ws.n_counters = 0;
-            return nullptr;
-        }
-        cudaMemsetAsync(e->ws.counters, 0, want * sizeof(int), stream);
-        e->ws.n_counters = want;
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    e = lru;
+    if (e->used) {
+        // evict: cudaFree waits for the device, so no kernel can still be using the block
+        int prev = dev;
+        cudaSetDevice(e->device);
+        cudaFree(e->ws.ptr);
+        cudaFree(e->ws.counters);
+        cudaSetDevice(prev);
+        e->used = false;
     }
+    Workspace w{};
+    bool ok = cudaMalloc(&w.ptr, kWsBytes) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&w.counters), kWsCounters * sizeof(int)) == cudaSuccess &&
+              cudaMemset(w.counters, 0, kWsCounters * sizeof(int)) == cudaSuccess;  // synchronous: visible to every stream
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    if (!ok) {
+        (void)cudaGetLastError();
+        if (w.ptr) cudaFree(w.ptr);
+        if (w.counters) cudaFree(w.counters);
+        return nullptr;
+    }
+    w.bytes = kWsBytes;
+    w.n_counters = kWsCounters;
+    e->ws = w;
+    e->device = dev;
+    e->stream = stream;
+    e->used = true;
+    e->stamp = ++g_ws_clock;
     return &e->ws;
 }
 
@@ -923,14 +932,18 @@ template <typename T, int QT, int MT, int CL, bool PAIR = false, bool D16 = fals
 bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     using Cfg = StageCfg<MT, PAIR>;
     constexpr size_t smem_bytes = 1024 /*align slack*/ + size_t(Cfg::kStages) * Cfg::kStageBytes + 256 /*barriers*/;
-    static bool attr_set = false;
+    // the shared-memory opt-in and the resident-CTA count are PER DEVICE (one process may drive several GPUs)
+    static bool attr_set[64] = {};
+    static int wave_ctas_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
     auto kern = gemm4_tc_kernel<T, QT, MT, CL, PAIR, D16>;
-    if (!attr_set) {
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("gemm4_tc smem attr", cudaGetLastError());
             return false;
         }
-        attr_set = true;
+        attr_set[dev] = true;
     }
     CUtensorMap tmap, tmap_w;
     if (!encode_tmap_2d(&tmap, A, 2, 128, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)(MT / CL), 64u)) {
@@ -951,7 +964,7 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     // in split order).  Every region size is a multiple of the cluster size.
     // CTAs that can be resident at once: SM count for CL == 1; for clusters the hardware may strand a
     // few SMs (GPC granularity), so ask the occupancy API.
-    static int wave_ctas = 0;
+    int& wave_ctas = wave_ctas_dev[dev];
     if (wave_ctas == 0) {
         wave_ctas = device_sm_count();
         if (CL > 1) {
@@ -980,7 +993,8 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     // Experimental persistent variant (see gemm4_tc_persistent_kernel): more tiles than SMs, no clusters.
     if constexpr (CL == 1 && MT >= 128 && !PAIR && !D16) {
         if (persistent_enabled() && tiles > sms) {
-            static bool pattr_set = false;
+            static bool pattr_set_dev[64] = {};
+            bool& pattr_set = pattr_set_dev[dev];
             auto pkern = gemm4_tc_persistent_kernel<T, QT, MT>;
             if (!pattr_set) {
                 if (cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) !=
@@ -1051,13 +1065,24 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (split_slots > 0) {
+        // the splits of a tile rendezvous in the epilogue: a COOPERATIVE launch makes the runtime schedule the
+        // whole (<= one wave) grid at once, so the wait cannot starve behind other streams' kernels
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_w, p);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
@@ -1069,6 +1094,24 @@ bool launch_mt(const T* A, Gemm4Params& p, cudaStream_t stream) {
 }
 
 } // namespace
+
+struct Gemm4Workspace {
+    float* partial;
+    int* counters;
+};
+bool gemm4_get_workspace(cudaStream_t stream, size_t partial_bytes, size_t n_counters, Gemm4Workspace* out) {
+    Workspace* ws = get_workspace(stream, partial_bytes, n_counters);
+    if (ws == nullptr) return false;
+    out->partial = reinterpret_cast<float*>(ws->ptr);
+    out->counters = ws->counters;
+    return true;
+}
+
+template <typename T>
+bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
+                       const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
+                       int ldc, int blocksize, int quant_type, cudaStream_t stream, void* const* peers, int n_peers,
+                       int mt_override, int force_splits, long long* trace);
 
 // Returns true if the tensor-core path handled the call.
 // `peers` / `n_peers`: up to 7 additional output bases (same ldc) that receive a copy of every element.
@@ -1082,6 +1125,19 @@ bool launch_gemm4_tc(const T* A, const uint8_t* B, const float* absmax, const ui
     if (blocksize < 32 || (blocksize & (blocksize - 1)) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(B) & 15) != 0) return false;
     if (quant_type != kNF4 && quant_type != kFP4) return false;
+
+    // Large token counts: the CTA-pair kernel (gemm4_pair.cu).  BNB_B200_PAIR_KERNEL=0 keeps the one-CTA kernel.
+    {
+        static int use_pair = -1;
+        if (use_pair < 0) {
+            const char* e = getenv("BNB_B200_PAIR_KERNEL");
+            use_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        if (use_pair && M >= 512 &&
+            launch_gemm4_pair<T>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc,
+                                 blocksize, quant_type, stream, peers, n_peers, 0, 0, nullptr))
+            return true;
+    }
 
     int MT = 256;
     if (M <= 16) MT = 16;

@@ -146,6 +146,12 @@ int cbnb_b200_gemm_4bit_path(int M, int N, int K, int blocksize, int dtype);
 /* Force a path for the next calls on this thread (-1 = automatic). */
 void cbnb_b200_gemm_4bit_force_path(int path);
 
+/* Developer / test entry for the CTA-pair (cta_group::2) large-M kernel (csrc/gemm4_pair.cu): explicit token
+ * tile mt (128 | 256 | 384; 0 = automatic), forced K split (0 = production rule; s = every tile s ways;
+ * 100 + s = only the partial last wave), optional event trace (device buffer of 2*10*256 int64 clocks, or NULL).
+ * Returns 0, or 100 when the shape is not served by that kernel. */
+int cbnb_b200_gemm_4bit_pair(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset, void* out, const void* bias, int M, int N, int K, int ldc, int blocksize, int quant_type, int dtype, int mt, int force_splits, long long* trace, bnb_stream_t stream);
+
 /* Strided-output variant used by the column-sharded linear: out has row stride ldc
  * (elements), so a shard writes its [M, N_shard] block into the gathered [M, N]. */
 void cbnb_b200_gemm_4bit_strided(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset, void* out, const void* bias, int M, int N, int K, int ldc, int blocksize, int quant_type, int dtype, bnb_stream_t stream);

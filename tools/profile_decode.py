@@ -1,7 +1,7 @@
 import os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transformers import LlamaConfig, LlamaForCausalLM
-from bitsandbytes_b200.bench_e2e import swap_linears
+from benchmarks.llama import swap_linears
 dev = torch.device("cuda")
 cfg = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=4, num_attention_heads=32,
                   num_key_value_heads=8, vocab_size=128256, max_position_embeddings=8192, tie_word_embeddings=False)

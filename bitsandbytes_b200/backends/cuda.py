@@ -368,8 +368,12 @@ def _int8_vectorwise_quant(A: torch.Tensor, threshold=0.0):
     outlier_cols = None
     if flags is not None:
         outlier_cols = torch.nonzero(flags).view(-1)  # data-dependent shape: the one unavoidable sync
-        if outlier_cols.numel() and q.numel() // q.shape[-1] > 1:
-            q.view(-1, q.shape[-1])[:, outlier_cols] = 0
+        rows = q.numel() // q.shape[-1]
+        if outlier_cols.numel() and rows > 1:
+            with _on_device(q):
+                lib.cbnb_b200_int8_zero_columns(q.data_ptr(), outlier_cols.data_ptr(), int(outlier_cols.numel()), rows,
+                                                q.shape[-1], _stream(q))
+            lib.check("int8_vectorwise_quant (outlier columns)")
     return q, row_stats, outlier_cols
 
 
@@ -421,19 +425,60 @@ def _int8_scaled_mm(A, B, row_stats, col_stats, bias=None, dtype=None):
     return torch.ops.bitsandbytes.int8_mm_dequant.default(acc, row_stats, col_stats, dtype=dtype, bias=bias)
 
 
+def _fused_mixed_mm(A, CA, CB, SCA, SCB, outlier_cols, bias):
+    """The whole LLM.int8() decomposition in two launches: one gathers subA and dequantises the outlier weight
+    columns into [N, jpad], the other is the int8 tcgen05 GEMM whose epilogue adds the outlier term.
+    Returns (out, subA) or None when the shape is not served (K % 16, > 64 outlier columns, dtype)."""
+    dtype = A.dtype
+    if dtype not in (torch.float16, torch.bfloat16) or CA.dtype != torch.int8 or CB.dtype != torch.int8:
+        return None
+    if SCA.dtype != torch.float32 or SCB.dtype != torch.float32:
+        return None
+    if bias is not None and bias.dtype != dtype:
+        return None
+    N, K = CB.shape
+    M = CA.numel() // K
+    J = int(outlier_cols.numel())
+    if K % 16 != 0 or M == 0 or J == 0 or J > 64:
+        return None
+    jpad = -(-J // 8) * 8
+    A2 = A.reshape(-1, K).contiguous()
+    CA = CA.contiguous()
+    CB = CB.contiguous()
+    SCA = SCA.contiguous()
+    SCB = SCB.contiguous()
+    cols = outlier_cols.to(torch.int64).contiguous()
+    subA_pad = torch.empty((M, jpad), device=A.device, dtype=dtype)
+    subBT = torch.empty((N, jpad), device=A.device, dtype=dtype)
+    out = torch.empty((*CA.shape[:-1], N), device=A.device, dtype=dtype)
+    with _on_device(A):
+        lib.cbnb_b200_int8_outlier_prep(A2.data_ptr(), CB.data_ptr(), SCB.data_ptr(), cols.data_ptr(), J, jpad, M, N, K,
+                                        _DTYPE_ID[dtype], subA_pad.data_ptr(), subBT.data_ptr(), _stream(A))
+        rc = lib.cbnb_b200_int8_mixed_mm(CA.data_ptr(), CB.data_ptr(), SCA.data_ptr(), SCB.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, subA_pad.data_ptr(),
+                                         subBT.data_ptr(), jpad, out.data_ptr(), M, N, K, _DTYPE_ID[dtype], _stream(A))
+    lib.check("int8_mixed_scaled_mm")
+    if rc != 0:
+        return None
+    subA = subA_pad[:, :J].reshape(*A.shape[:-1], J)
+    return out, (subA if jpad == J else subA.contiguous())
+
+
 @kernel("int8_mixed_scaled_mm")
 def _int8_mixed_scaled_mm(A, CA, CB, SCA, SCB, outlier_cols=None, bias=None):
     """LLM.int8() forward: int8 part + the fp16/bf16 outlier columns (reference default/ops.py:64-100)."""
-    subB = None
-    subA = None
     if outlier_cols is not None and outlier_cols.numel():
+        fused = _fused_mixed_mm(A, CA, CB, SCA, SCB, outlier_cols, bias)
+        if fused is not None:
+            return fused
+        # shapes the fused kernel does not take (> 64 outlier columns, K % 16 != 0): the reference's own chain
         subA = A[..., outlier_cols].contiguous()
         # reference _ops.py:118-121: CB * SCB * (1/127) in fp32, then to A.dtype
         subB = torch.ops.bitsandbytes.int8_vectorwise_dequant.default(CB[:, outlier_cols].contiguous(), SCB)
         subB = subB.to(A.dtype).t()
-    else:
-        subA = torch.empty(0, device=A.device, dtype=A.dtype)  # keeps torch.compile's output arity fixed
-    out = torch.ops.bitsandbytes.int8_scaled_mm.default(CA, CB, SCA, SCB, bias=bias, dtype=A.dtype)
-    if subB is not None:
+        out = torch.ops.bitsandbytes.int8_scaled_mm.default(CA, CB, SCA, SCB, bias=bias, dtype=A.dtype)
         out = out.view(-1, out.shape[-1]).addmm(subA.view(-1, subA.shape[-1]), subB).view(out.shape)
+        return out, subA
+    subA = torch.empty(0, device=A.device, dtype=A.dtype)  # keeps torch.compile's output arity fixed
+    out = torch.ops.bitsandbytes.int8_scaled_mm.default(CA, CB, SCA, SCB, bias=bias, dtype=A.dtype)
     return out, subA

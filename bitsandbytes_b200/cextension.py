@@ -66,6 +66,12 @@ def _signatures():
     sig["cbnb_b200_gemm_4bit_multi_out"] = ([_VOIDP] * 7 + [_I32] + [_VOIDP] + [_I32] * 7 + [_VOIDP], _I32)
     # (CA, CB, SCA, SCB, bias, out, M, N, K, dtype, stream) -> int
     sig["cbnb_b200_int8_scaled_mm"] = ([_VOIDP] * 6 + [_I32] * 4 + [_VOIDP], _I32)
+    # (CA, CB, SCA, SCB, bias, subA, subBT, jpad, out, M, N, K, dtype, stream) -> int
+    sig["cbnb_b200_int8_mixed_mm"] = ([_VOIDP] * 7 + [_I32] + [_VOIDP] + [_I32] * 4 + [_VOIDP], _I32)
+    # (A, CB, SCB, cols, J, jpad, M, N, K, dtype, subA, subBT, stream)
+    sig["cbnb_b200_int8_outlier_prep"] = ([_VOIDP] * 4 + [_I32] * 6 + [_VOIDP] * 3, None)
+    # (CA, cols, J, rows, K, stream)
+    sig["cbnb_b200_int8_zero_columns"] = ([_VOIDP] * 2 + [_I32] * 3 + [_VOIDP], None)
     # (A, out, rowStats, col_flags, threshold, rows, cols, dtype, stream)
     sig["cbnb_b200_int8_vector_quant_flags"] = ([_VOIDP] * 4 + [ct.c_float] + [_I32] * 3 + [_VOIDP], None)
     sig["cget_managed_ptr"] = ([ct.c_size_t], _VOIDP)

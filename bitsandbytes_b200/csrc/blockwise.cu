@@ -16,8 +16,10 @@
 //   code    = decision procedure on mul.ftz(x, inv)
 //   dequant = T( mul.ftz(value(code), absmax) )                 [one rounding]
 #include "common.cuh"
+#include "decode4.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace bnb200 {
 
@@ -398,33 +400,30 @@ void launch_quantize_blockwise_impl(const float* code, const T* A, float* absmax
 // dequantize
 // =====================================================================================
 //
-// Every thread produces 16 bytes of output per step (8 x 16-bit or 4 x fp32), lanes on
-// consecutive 16-byte slots; kDqUnroll independent steps are issued back to back so the
-// loads of all of them are in flight before the first store.
-
 constexpr int kDqThreads = 256;
-constexpr int kDqUnroll = 4;
+constexpr int kDqUnroll = 8;
 
+// 8-bit codes (any output type) and 4-bit codes -> fp32.  Every thread produces 16 bytes of output per step
+// (8 x 16-bit or 4 x fp32), lanes on consecutive 16-byte slots; kDqUnroll independent steps are in flight per
+// thread and the loads of the NEXT round are issued before the current round is decoded (software pipeline),
+// the first round before the look-up table is even built -- so the table's own fetch (a cold 1 KB read) overlaps
+// the data instead of delaying it.
 template <typename T, int QT>
 __global__ void __launch_bounds__(kDqThreads)
     dequantize_blockwise_kernel(const float* __restrict__ code, const uint8_t* __restrict__ A,
                                 const float* __restrict__ absmax, T* __restrict__ out, int log2_bs,
                                 long long n_vec /* number of full 16-byte output vectors */) {
     constexpr int OE = 16 / DT<T>::kBytes; // output elements per vector: 8 or 4
-    // 4-bit: byte -> (value(hi nibble), value(lo nibble)).  8-bit: the 256-entry code book.
-    __shared__ float2 lut2[256];
-    __shared__ float scode[256];
-    if (QT == kGeneral8bit) {
-        scode[threadIdx.x] = code[threadIdx.x];
-    } else {
-        lut2[threadIdx.x] = make_float2(code4_value<QT>(threadIdx.x >> 4), code4_value<QT>(threadIdx.x & 15u));
-    }
-    __syncthreads();
+    // 8-bit: the 256-entry code book.  4-bit (fp32 output only): 16 values, one private column per lane
+    // (index = code * 32 + lane): conflict-free by construction.
+    __shared__ float scode[QT == kGeneral8bit ? 256 : 16 * 32];
+    float creg = 0.f;
+    if (QT == kGeneral8bit) creg = __ldg(code + threadIdx.x);
 
     const long long stride = (long long)gridDim.x * kDqThreads * kDqUnroll;
-    for (long long v0 = (long long)blockIdx.x * kDqThreads * kDqUnroll + threadIdx.x; v0 < n_vec; v0 += stride) {
-        uint32_t packed[kDqUnroll][2];
-        float s[kDqUnroll];
+    uint32_t packed[kDqUnroll][2];
+    float s[kDqUnroll];
+    auto load = [&](long long v0) {
 #pragma unroll
         for (int u = 0; u < kDqUnroll; ++u) {
             const long long v = v0 + (long long)u * kDqThreads;
@@ -449,6 +448,31 @@ __global__ void __launch_bounds__(kDqThreads)
                 s[u] = __ldg(absmax + (e0 >> log2_bs));
             }
         }
+    };
+    long long v0 = (long long)blockIdx.x * kDqThreads * kDqUnroll + threadIdx.x;
+    load(v0);
+    if (QT == kGeneral8bit) {
+        scode[threadIdx.x] = creg;
+    } else {
+        const int lane = threadIdx.x & 31;
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) scode[c * 32 + lane] = code4_value<QT>(c);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+
+    for (; v0 < n_vec; v0 += stride) {
+        uint32_t cur[kDqUnroll][2];
+        float cs[kDqUnroll];
+#pragma unroll
+        for (int u = 0; u < kDqUnroll; ++u) {
+            cur[u][0] = packed[u][0];
+            cur[u][1] = packed[u][1];
+            cs[u] = s[u];
+        }
+        if (v0 + stride < n_vec) load(v0 + stride);
 #pragma unroll
         for (int u = 0; u < kDqUnroll; ++u) {
             const long long v = v0 + (long long)u * kDqThreads;
@@ -457,16 +481,15 @@ __global__ void __launch_bounds__(kDqThreads)
                 if (QT == kGeneral8bit) {
 #pragma unroll
                     for (int e = 0; e < OE; ++e) {
-                        uint32_t q = (packed[u][e >> 2] >> (8 * (e & 3))) & 0xffu;
-                        f[e] = mul_ftz(scode[q], s[u]);
+                        uint32_t q = (cur[u][e >> 2] >> (8 * (e & 3))) & 0xffu;
+                        f[e] = mul_ftz(scode[q], cs[u]);
                     }
                 } else {
 #pragma unroll
-                    for (int b = 0; b < OE / 2; ++b) {
-                        uint32_t byte = (packed[u][0] >> (8 * b)) & 0xffu;
-                        float2 c = lut2[byte];
-                        f[2 * b] = mul_ftz(c.x, s[u]);
-                        f[2 * b + 1] = mul_ftz(c.y, s[u]);
+                    for (int e = 0; e < OE; ++e) {
+                        // element 2b sits in the high nibble of byte b
+                        uint32_t q = (cur[u][0] >> (8 * (e >> 1) + ((e & 1) ? 0 : 4))) & 0xfu;
+                        f[e] = mul_ftz(scode[q * 32 + lane], cs[u]);
                     }
                 }
                 uint4 o;
@@ -480,6 +503,65 @@ __global__ void __launch_bounds__(kDqThreads)
                 stg_stream_v4(out + v * OE, o);
             }
         }
+    }
+}
+
+// 4-bit -> fp16 / bf16 (the weight path of Linear4bit): register-table decode, no shared-memory look-ups.
+//   * a lane owns 64 consecutive elements (32 bytes of codes = two 16-byte loads; one quantisation block at the
+//     default block size, half of one / several of them for other block sizes -- always whole tables): it
+//     builds the 16-entry table rn_T(value * scale) once (decode4.cuh: 16 FMUL + 8 packed roundings, exactly the
+//     reference's one-rounding result) and translates the codes with PRMT only;
+//   * the 128 bytes a lane produces go through a per-warp 4 KB staging tile (16-byte chunks XOR-swizzled by the
+//     row, so both the lane-major writes and the row-major reads are bank-conflict-free) and leave as fully
+//     coalesced 512-byte warp stores;
+//   * grid = a multiple of the SM count, several CTAs per SM: each thread has 32 B of codes + its scale in
+//     flight, i.e. > 32 KB of reads per SM, which covers the HBM latency-bandwidth product.
+constexpr int kD4Warps = 8;
+
+template <typename T, int QT>
+__global__ void __launch_bounds__(kD4Warps * 32, 4)
+    dequantize4_prmt_kernel(const uint8_t* __restrict__ A, const float* __restrict__ absmax, T* __restrict__ out,
+                            int log2_bs, long long n_units /* 64-element units */) {
+    __shared__ __align__(128) uint8_t stage[kD4Warps][4096];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool two = log2_bs == 5;
+    uint8_t* tile = stage[warp];
+    const long long step = (long long)gridDim.x * kD4Warps * 32;
+    for (long long u0 = ((long long)blockIdx.x * kD4Warps + warp) * 32; u0 < n_units; u0 += step) {
+        const long long u = u0 + lane;
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        float s0 = 0.f, s1 = 0.f;
+        if (u < n_units) {
+            // default caching: the two halves of a 32-byte sector are fetched by consecutive instructions
+            q0 = __ldg(reinterpret_cast<const uint4*>(A + u * 32));
+            q1 = __ldg(reinterpret_cast<const uint4*>(A + u * 32 + 16));
+            s0 = __ldg(absmax + ((u * 64) >> log2_bs));
+            if (two) s1 = __ldg(absmax + ((u * 64 + 32) >> log2_bs));
+        }
+        uint32_t r[32];
+        DecodeTable tab;
+        build_table<T, QT>(s0, tab);
+        decode_word(q0.x, tab, r + 0);
+        decode_word(q0.y, tab, r + 4);
+        decode_word(q0.z, tab, r + 8);
+        decode_word(q0.w, tab, r + 12);
+        if (two) build_table<T, QT>(s1, tab);
+        decode_word(q1.x, tab, r + 16);
+        decode_word(q1.y, tab, r + 20);
+        decode_word(q1.z, tab, r + 24);
+        decode_word(q1.w, tab, r + 28);
+        uint8_t* row = tile + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int rr = 4 * k + (lane >> 3), q = lane & 7;  // 16-byte chunk 32 k + lane of the warp's 4 KB
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((q ^ (rr & 7)) << 4));
+            if (u0 + rr < n_units) stg_stream_v4(out + (u0 + rr) * 64 + q * 8, v);
+        }
+        __syncwarp();
     }
 }
 
@@ -513,6 +595,24 @@ void launch_dequantize_blockwise(const float* code, const uint8_t* A, const floa
     long long n_vec = 0;
     if (pow2 && aligned && blocksize >= OE) n_vec = n / OE;
     const int sms = device_sm_count();
+    if constexpr (QT != kGeneral8bit && !std::is_same<T, float>::value) {
+        // 4-bit -> 16-bit: the register-table kernel on the whole 64-element units, the generic kernel on the tail
+        const bool a16 = (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+        if (pow2 && aligned && a16 && blocksize >= 32 && n >= 64) {
+            const long long n_units = n / 64;
+            const long long want = (n_units + kD4Warps * 32 - 1) / (kD4Warps * 32);
+            const int grid = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);  // 4 resident CTAs per SM
+            dequantize4_prmt_kernel<T, QT><<<grid, kD4Warps * 32, 0, stream>>>(A, absmax, out, ilog2_pow2(blocksize), n_units);
+            BNB200_CHECK_LAUNCH("dequantize4_prmt");
+            n_vec = 0;
+            const long long first4 = n_units * 64;
+            if (first4 < n) {
+                dequantize_blockwise_generic_kernel<T, QT><<<1, 256, 0, stream>>>(code, A, absmax, out, blocksize, first4, n);
+                BNB200_CHECK_LAUNCH("dequantize_blockwise_generic");
+            }
+            return;
+        }
+    }
     if (n_vec > 0) {
         long long per_cta = (long long)kDqThreads * kDqUnroll;
         long long want = (n_vec + per_cta - 1) / per_cta;

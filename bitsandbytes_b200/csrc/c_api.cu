@@ -46,7 +46,11 @@ void launch_int8_vector_quant(const void* A, int8_t* out, float* rowStats, int* 
 void launch_dequant_mm_int32_fp16(const int* A, const float* rowStats, const float* colStats, __half* out,
                                   const __half* bias, int numRows, int numCols, cudaStream_t stream);
 int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const float* SCA, const float* SCB,
-                     const void* bias, int M, int N, int K, int ldc, int epi, cudaStream_t stream);
+                     const void* bias, int M, int N, int K, int ldc, int epi, cudaStream_t stream,
+                     const void* subA = nullptr, const void* subBT = nullptr, int jpad = 0);
+void launch_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J, int jpad,
+                              int M, int N, int K, int dtype, void* subA, void* subBT, cudaStream_t stream);
+void launch_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream);
 
 // ---------------------------------------------------------------- error plumbing
 namespace {
@@ -407,6 +411,33 @@ int cbnb_b200_int8_scaled_mm(const int8_t* CA, const int8_t* CB, const float* SC
                              void* out, int M, int N, int K, int dtype, cudaStream_t stream) {
     if (dtype != 1 && dtype != 2) return 100;
     return launch_int8_gemm(CA, CB, out, SCA, SCB, bias, M, N, K, N, dtype, stream);
+}
+
+// LLM.int8() mixed decomposition in one GEMM launch: the int8 part as above plus, in the same epilogue, the
+// outlier term subA[M, jpad] . subBT[N, jpad]^T (both of the output type, built by cbnb_b200_int8_outlier_prep).
+int cbnb_b200_int8_mixed_mm(const int8_t* CA, const int8_t* CB, const float* SCA, const float* SCB, const void* bias,
+                            const void* subA, const void* subBT, int jpad, void* out, int M, int N, int K, int dtype,
+                            cudaStream_t stream) {
+    if (dtype != 1 && dtype != 2) return 100;
+    return launch_int8_gemm(CA, CB, out, SCA, SCB, bias, M, N, K, N, dtype, stream, subA, subBT, jpad);
+}
+
+void cbnb_b200_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J,
+                                 int jpad, int M, int N, int K, int dtype, void* subA, void* subBT,
+                                 cudaStream_t stream) {
+    if (dtype != 1 && dtype != 2) {
+        set_last_error_msg("int8_outlier_prep: dtype must be 1 (fp16) or 2 (bf16)");
+        return;
+    }
+    if (J < 0 || jpad < J || (jpad % 8) != 0) {
+        set_last_error_msg("int8_outlier_prep: need 0 <= J <= jpad, jpad a multiple of 8");
+        return;
+    }
+    launch_int8_outlier_prep(A, CB, SCB, cols, J, jpad, M, N, K, dtype, subA, subBT, stream);
+}
+
+void cbnb_b200_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream) {
+    launch_int8_zero_columns(CA, cols, J, rows, K, stream);
 }
 
 void cdequant_mm_int32_fp16(int* A, float* rowStats, float* colStats, __half* out, __half* bias, int numRows,

@@ -165,9 +165,74 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ======================================================================================
+// outlier decomposition glue (reference backends/default/ops.py:79-90 does this with torch indexing,
+// int8_vectorwise_dequant and .t()): one launch gathers the outlier columns of the activations,
+//     subA[m, j]  = A[m, cols[j]]                                  (zero-padded to jpad columns)
+// and dequantises the matching weight columns, already in the [N, jpad] layout the GEMM epilogue reads,
+//     subBT[n, j] = T( (float(CB[n, cols[j]]) * SCB[n]) * (1/127) )  (reference _ops.py:118-121: fp32, then A.dtype)
+// ======================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+    int8_outlier_prep_kernel(const T* __restrict__ A, const int8_t* __restrict__ CB, const float* __restrict__ SCB,
+                             const long long* __restrict__ cols, int J, int jpad, int M, int N, int K,
+                             T* __restrict__ subA, T* __restrict__ subBT) {
+    const long long total = (long long)(M + N) * jpad;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / jpad;
+        const int j = (int)(idx - r * jpad);
+        const long long col = j < J ? cols[j] : 0;
+        if (r < M) {
+            subA[idx] = j < J ? A[r * K + col] : DT<T>::from_f32(0.f);
+        } else {
+            const long long n = r - M;
+            float v = 0.f;
+            if (j < J) v = __fmul_rn(__fmul_rn((float)CB[n * K + col], __ldg(SCB + n)), 7.874015718698502e-3f);
+            subBT[n * jpad + j] = DT<T>::from_f32(v);
+        }
+    }
+}
+
+// CA[:, cols[j]] = 0 for every outlier column (reference backends/cuda/ops.py:233-236, a torch index_put there)
+__global__ void __launch_bounds__(256)
+    int8_zero_columns_kernel(int8_t* __restrict__ CA, const long long* __restrict__ cols, int J, int rows, int K) {
+    const long long total = (long long)rows * J;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / J;
+        CA[r * K + cols[idx - r * J]] = 0;
+    }
+}
+
 } // namespace
 
 // ---------------------------------------------------------------- launch wrappers
+void launch_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J, int jpad,
+                              int M, int N, int K, int dtype, void* subA, void* subBT, cudaStream_t stream) {
+    if (jpad <= 0 || M + N <= 0) return;
+    const long long total = (long long)(M + N) * jpad;
+    long long want = (total + 255) / 256;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    if (dtype == 1)
+        int8_outlier_prep_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)A, CB, SCB, cols, J, jpad, M, N, K,
+                                                                   (__half*)subA, (__half*)subBT);
+    else
+        int8_outlier_prep_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)A, CB, SCB, cols, J, jpad,
+                                                                          M, N, K, (__nv_bfloat16*)subA,
+                                                                          (__nv_bfloat16*)subBT);
+    BNB200_CHECK_LAUNCH("int8_outlier_prep");
+}
+
+void launch_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream) {
+    if (J <= 0 || rows <= 0) return;
+    const long long total = (long long)rows * J;
+    long long want = (total + 255) / 256;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    int8_zero_columns_kernel<<<grid, 256, 0, stream>>>(CA, cols, J, rows, K);
+    BNB200_CHECK_LAUNCH("int8_zero_columns");
+}
+
 void launch_int8_vector_quant(const void* A, int8_t* out, float* rowStats, int* col_flags, float threshold, int rows,
                               int cols, int dtype /*1 fp16, 2 bf16*/, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return;

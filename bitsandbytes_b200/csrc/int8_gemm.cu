@@ -5,7 +5,10 @@
 // epilogue either stores int32 (cigemmlt_32 ABI) or applies the dequantisation of reference
 // kdequant_mm_int32_fp16 (csrc/kernels.cu:1396-1448),
 //     fp16/bf16( fma(acc * SCA[m] * SCB[n], 1/127^2, bias[n]) ),
-// in-kernel, which removes the 2 x M x N x 4-byte int32 round trip through HBM.
+// in-kernel, which removes the 2 x M x N x 4-byte int32 round trip through HBM -- and, for LLM.int8()'s
+// mixed decomposition (reference backends/default/ops.py:64-100: `output.addmm(subA, subB)` after the int8
+// matmul), adds the OUTLIER term  sum_j subA[m, j] * subB[j, n]  (fp16/bf16 products, fp32 accumulation)
+// in the same epilogue, so the second pass over out[M, N] and the cuBLAS call of the reference chain are gone.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -58,12 +61,32 @@ struct I8Params {
     const float* SCA;   // [M]  row stats of the activations
     const float* SCB;   // [N]  row stats of the weights
     const void* bias;   // T[N] or NULL
+    const void* subA;   // T[M, jpad]  outlier columns of the activations (zero-padded to jpad), or NULL
+    const void* subBT;  // T[N, jpad]  dequantised weight columns CB[:, cols] * SCB / 127, or NULL
+    int jpad;           // padded outlier count (multiple of 8, <= JMAX)
     int M, N, K, ldc;
     int kblocks;
     int n_tiles, m_pairs, pair_tiles;
 };
 
-template <int EPI, bool PAIR, int KSUB>
+// 8 consecutive T -> fp32
+template <int EPI> __device__ __forceinline__ void i8_unpack8(const uint4& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (EPI == 1) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        } else {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+}
+
+// JMAX: capacity of the fused outlier term (0 = none): the thread keeps its row of subA in JMAX registers.
+template <int EPI, bool PAIR, int KSUB, int JMAX>
 __global__ void __launch_bounds__(kI8Threads, 1)
     int8_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const I8Params p) {
@@ -233,6 +256,41 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             }
             float sca = 0.f;
             if (EPI != 0 && m_ok) sca = __ldg(p.SCA + m);
+            // this token's outlier activations (fp32 copies of the T values: the products below are exact)
+            float oa[JMAX > 0 ? JMAX : 1];
+            if constexpr (JMAX > 0) {
+#pragma unroll
+                for (int g = 0; g < JMAX / 8; ++g) {
+                    float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (m_ok && 8 * g < p.jpad)
+                        i8_unpack8<EPI>(__ldg(reinterpret_cast<const uint4*>(
+                                            reinterpret_cast<const uint16_t*>(p.subA) + (long long)m * p.jpad + 8 * g)),
+                                        t8);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) oa[8 * g + e] = t8[e];
+                }
+            }
+            // outlier term of output feature n for this token: sum_j subA[m, j] * subBT[n, j]
+            // (every lane of the warp reads the same subBT row: one broadcast sector per load, L1-resident)
+            auto outlier = [&](int n) -> float {
+                float o = 0.f;
+                if constexpr (JMAX > 0) {
+                    if (n < p.N) {
+                        const uint4* brow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.subBT) +
+                                                                           (long long)n * p.jpad);
+#pragma unroll
+                        for (int g = 0; g < JMAX / 8; ++g) {
+                            if (8 * g < p.jpad) {
+                                float b8[8];
+                                i8_unpack8<EPI>(__ldg(brow + g), b8);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) o = fmaf(oa[8 * g + e], b8[e], o);
+                            }
+                        }
+                    }
+                }
+                return o;
+            };
             ptx::mbar_wait_bounded(&tmem_full[acc], (tcount >> 1) & 1u, 4, (int)tcount, pt);
             ptx::tc_fence_after();
             const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * kI8TileN;
@@ -269,8 +327,14 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 #pragma unroll
                     for (int t = 0; t < 32; t += 2) {
                         if (EPI == 1) {
-                            const float f0 = dequant_value((int)v[t], sca, scb[c + t], sbias[c + t]);
-                            const float f1 = dequant_value((int)v[t + 1], sca, scb[c + t + 1], sbias[c + t + 1]);
+                            float f0 = dequant_value((int)v[t], sca, scb[c + t], sbias[c + t]);
+                            float f1 = dequant_value((int)v[t + 1], sca, scb[c + t + 1], sbias[c + t + 1]);
+                            if constexpr (JMAX > 0) {
+                                // reference: the int8 result is an fp16 tensor, then addmm adds the fp32-accumulated
+                                // outlier product and rounds once more
+                                f0 = __half2float(__float2half_rn(f0)) + outlier(n + t);
+                                f1 = __half2float(__float2half_rn(f1)) + outlier(n + t + 1);
+                            }
                             w[t >> 1] = pack2<__half>(f0, f1);
                         } else {
                             // bf16 output, bit-identical to the reference chain (backends/cuda/ops.py:186-210):
@@ -282,6 +346,10 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                             if (p.bias != nullptr) {
                                 f0 = __half2float(__float2half_rn(f0 + sbias[c + t]));
                                 f1 = __half2float(__float2half_rn(f1 + sbias[c + t + 1]));
+                            }
+                            if constexpr (JMAX > 0) {
+                                f0 = __bfloat162float(__float2bfloat16_rn(f0)) + outlier(n + t);
+                                f1 = __bfloat162float(__float2bfloat16_rn(f1)) + outlier(n + t + 1);
                             }
                             w[t >> 1] = pack2<__nv_bfloat16>(f0, f1);
                         }
@@ -312,19 +380,21 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     }
 }
 
-template <int EPI, bool PAIR, int KSUB>
+template <int EPI, bool PAIR, int KSUB, int JMAX = 0>
 int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
     using Cfg = I8Cfg<PAIR, KSUB>;
     constexpr size_t smem_bytes = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + 4096 + 256;
-    static bool attr_set = false;
-    auto kern = int8_gemm_tc_kernel<EPI, PAIR, KSUB>;
+    static bool attr_set[64] = {};  // the shared-memory opt-in is per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    auto kern = int8_gemm_tc_kernel<EPI, PAIR, KSUB, JMAX>;
     p.kblocks = (p.K + KSUB * kI8BK - 1) / (KSUB * kI8BK);
-    if (!attr_set) {
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
             set_last_error("int8_gemm_tc smem attr", cudaGetLastError());
             return 1;
         }
-        attr_set = true;
+        attr_set[dev] = true;
     }
     p.n_tiles = (p.N + kI8TileN - 1) / kI8TileN;
     const int m_tiles = (p.M + kI8TileM - 1) / kI8TileM;
@@ -357,11 +427,15 @@ int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStr
 } // namespace
 
 // epi: 0 int32, 1 fp16, 2 bf16.  Returns 0 ok, 100 "not implemented for this shape".
+// subA / subBT / jpad: the fused outlier term (epi 1 / 2 only; jpad a multiple of 8, <= 64), or NULL / 0.
 int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const float* SCA,
                                 const float* SCB, const void* bias, int M, int N, int K, int ldc, int epi,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const void* subA, const void* subBT, int jpad) {
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (K % 16) != 0) return 100;
+    if (jpad != 0 && (epi == 0 || jpad < 0 || jpad > 64 || (jpad % 8) != 0 || subA == nullptr || subBT == nullptr ||
+                      (reinterpret_cast<uintptr_t>(subA) & 15) != 0 || (reinterpret_cast<uintptr_t>(subBT) & 15) != 0))
+        return 100;
     if ((reinterpret_cast<uintptr_t>(acts) & 15) != 0 || (reinterpret_cast<uintptr_t>(weights) & 15) != 0) return 100;
     CUtensorMap ta, tb;
     if (!encode_tmap_2d(&ta, acts, 1, 128, (uint64_t)M, (uint64_t)K, (uint64_t)K, kI8TileM, kI8BK)) return 100;
@@ -376,6 +450,22 @@ int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const
     p.N = N;
     p.K = K;
     p.ldc = ldc;
+    p.subA = subA;
+    p.subBT = subBT;
+    p.jpad = jpad;
+    if (jpad > 0) {
+        // fused outlier term: the pair kernel, capacity = next of {8, 16, 32, 64}
+#define BNB200_I8_J(E)                                                                                                 \
+        if (jpad <= 8) return launch_i8<E, true, 2, 8>(ta, tb, p, stream);                                             \
+        if (jpad <= 16) return launch_i8<E, true, 2, 16>(ta, tb, p, stream);                                           \
+        if (jpad <= 32) return launch_i8<E, true, 2, 32>(ta, tb, p, stream);                                           \
+        return launch_i8<E, true, 2, 64>(ta, tb, p, stream);
+        if (epi == 1) {
+            BNB200_I8_J(1)
+        }
+        BNB200_I8_J(2)
+#undef BNB200_I8_J
+    }
     // BNB_B200_I8_MODE=multicast selects the cta_group::1 variant (A/B measurements); default = pair
     static const bool pair = [] {
         const char* e = getenv("BNB_B200_I8_MODE");

@@ -161,6 +161,20 @@ void cbnb_b200_gemm_4bit_strided(const void* A, const uint8_t* B, const float* a
  * dtype 1 = fp16, 2 = bf16.  Returns 0 / 100 like cigemmlt_32. */
 int cbnb_b200_int8_scaled_mm(const int8_t* CA, const int8_t* CB, const float* SCA, const float* SCB, const void* bias, void* out, int M, int N, int K, int dtype, bnb_stream_t stream);
 
+/* LLM.int8() mixed decomposition (reference backends/default/ops.py:64-100) in ONE GEMM launch: the int8 part as
+ * cbnb_b200_int8_scaled_mm plus, in the same epilogue, the outlier term subA[M, jpad] . subBT[N, jpad]^T
+ * (operands of the output type, fp32 accumulation), added to the rounded int8 result and rounded once more, as
+ * the reference's `output.addmm(subA, subB)` does.  jpad: multiple of 8, <= 64.  Returns 0 / 100. */
+int cbnb_b200_int8_mixed_mm(const int8_t* CA, const int8_t* CB, const float* SCA, const float* SCB, const void* bias, const void* subA, const void* subBT, int jpad, void* out, int M, int N, int K, int dtype, bnb_stream_t stream);
+
+/* Builds the two operands of the outlier term in one launch: subA[m, j] = A[m, cols[j]] and
+ * subBT[n, j] = T((float(CB[n, cols[j]]) * SCB[n]) * (1/127))  (reference _ops.py:118-121), zero-padded from J to
+ * jpad columns.  cols: J int64 column indices on the device (torch.nonzero of the outlier flags). */
+void cbnb_b200_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J, int jpad, int M, int N, int K, int dtype, void* subA, void* subBT, bnb_stream_t stream);
+
+/* CA[:, cols[j]] = 0 for the J outlier columns (reference backends/cuda/ops.py:233-236). */
+void cbnb_b200_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, bnb_stream_t stream);
+
 /* Fused row quantisation + outlier-column detection without a host sync:
  * col_flags[c] = 1 if any |A[r,c]| >= threshold.  dtype 1 = fp16, 2 = bf16 (A is read as
  * that type; the reference kernel is fp16-only). */

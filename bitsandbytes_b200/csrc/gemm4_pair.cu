@@ -13,8 +13,10 @@
 // rebuilt around that:
 //   * a-stage = 64 k-elements = 32 TMEM columns of decoded weights per CTA.  The ring of a-stages (TMEM
 //     A slots + the matching activation slots in shared memory) has one `full` barrier per stage on the
-//     LEADER (TMA bytes of both CTAs + its own decode warps + one relayed arrival for the peer's) and one
-//     `empty` barrier per stage in each CTA (tcgen05.commit multicast).
+//     LEADER (TMA bytes of both CTAs + the decode warps of BOTH CTAs: the peer's warps arrive remotely with a
+//     relaxed cluster-scope arrive -- a cluster-scope RELEASE costs a MEMBAR.ALL.GPU, ~1300 cycles, and there is
+//     no generic-proxy memory to publish, only "my tcgen05.st has completed") and one `empty` barrier per
+//     stage in each CTA (tcgen05.commit multicast).
 //   * packed codes travel in their OWN, deeper ring (128 k-elements = 8 KB per stage, 8 stages) fed by a
 //     separate producer thread, so the decode warps run ahead of the tensor core instead of starting a
 //     stage's decode only after the MMA that frees the matching TMEM slot has retired.
@@ -26,12 +28,16 @@
 //     columns = the whole 512-column TMEM): a decoded weight feeds 384 MACs instead of 256, which takes
 //     the ALU pipe (the PRMT decode: ~2.9 ALU instructions per weight, 64 lanes/clk/SM) off the critical
 //     path.  MT = 256 (one N = 256 MMA, 8 stages) serves smaller token counts.
-//   * the partial last wave is split along K (2..4 ways); the splits of a tile exchange fp32 partials
-//     through an L2-resident workspace and the LAST ARRIVER (atomic counter, no spinning) sums them in
-//     split order -- deterministic, and safe under any co-scheduling.
+//   * epilogue: accumulators -> registers -> +bias -> T -> a row-major [tokens][128 features] tile in the
+//     (now idle) activation ring -> ONE TMA store per decode group (and per destination: the fused all-gather of
+//     the column-sharded layer is the same bulk store into each peer GPU's buffer, asynchronous, so the NVLink
+//     writes drain while the SM already runs its next CTA).  2-byte scalar stores took 15-23 k cycles per tile.
+//   * the partial last wave is split 2 ways along K; the two splits of a tile exchange one fp32 partial
+//     through an L2-resident workspace and the LAST ARRIVER (atomic counter, no spinning) adds the other
+//     half to its own accumulators -- a + b is commutative, so the result does not depend on who is last.
 //
-// Warp roles (608 threads): warp 0 activation producer (TMA), warp 1 MMA issuer (leader) / relay (peer)
-// + TMEM allocator, warps 2..17 decode then epilogue, warp 18 code producer (TMA).
+// Warp roles (608 threads): warp 0 activation producer (TMA), warp 1 MMA issuer (leader only) + TMEM
+// allocator, warps 2..17 decode then epilogue, warp 18 code producer (TMA).
 #include "common.cuh"
 #include "decode4.cuh"
 #include "sm100_ptx.cuh"
@@ -60,6 +66,11 @@ constexpr int kThreads = 32 * (2 + kDecodeWarps + 1);
 constexpr int kScaleDepth = 4;     // per-thread register ring of scales (stages of one group)
 constexpr int kTraceStages = 256;  // TRACE builds: events are kept for the first 256 a-stages of cluster 0
 constexpr int kTraceRoles = 10;
+constexpr int kMaxOuts = 8;        // local output + up to 7 peer buffers
+
+struct OutMaps {
+    CUtensorMap m[kMaxOuts];
+};
 
 struct PairParams {
     const uint8_t* B;
@@ -71,6 +82,7 @@ struct PairParams {
     void* out;
     void* peer_out[7];
     int n_peers;
+    int tma_out;         // 1: the epilogue stores through the OutMaps tensor maps (ldc % 8 == 0, aligned bases)
     float* ws_partial;   // [split slots][MT columns][128 rows] fp32
     int* ws_counter;     // one per split (tile, CTA rank); zero on entry, reset by the last arriver
     long long* trace;    // TRACE builds only
@@ -110,7 +122,7 @@ template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams&
 template <typename T, int QT, int MT, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const PairParams p) {
+                      const __grid_constant__ OutMaps omaps, const PairParams p) {
     using Cfg = PairCfg<MT>;
     constexpr int kNA = Cfg::kNA;
     constexpr int kXStageBytes = Cfg::kXStageBytes;
@@ -159,9 +171,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kNA; ++s) {
-            // leader: producer's expect_tx arrival + 4 decode warps + the peer's relayed arrival
-            // peer:   its 4 decode warps (the relay warp waits on it)
-            ptx::mbar_init(&full[s], leader ? 6 : 4);
+            // leader: producer's expect_tx arrival + the 4 decode warps of each CTA (the peer's never used)
+            ptx::mbar_init(&full[s], 9);
             ptx::mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < kNC; ++s) {
@@ -222,23 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else if (warp == 1) {
         int s = 0;
         uint32_t ph = 0;
-        if (!leader) {
-            // ============================================================== relay (peer CTA)
-            // "my decode group has filled A slot s": ONE cluster-scope arrive per stage on the leader's barrier
-            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
-            for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&full[s], ph, 3, i);
-                if (lane == 0) {
-                    ptx::mbar_arrive_cluster(lead_full0 + 8u * s);
-                    trace_ev<TRACE>(p, 7, i);
-                }
-                __syncwarp();
-                if (++s == kNA) {
-                    s = 0;
-                    ph ^= 1u;
-                }
-            }
-        } else {
+        if (leader) {
             // ============================================================== MMA issuer (leader CTA)
             constexpr uint32_t idesc =
                 ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
@@ -284,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t sw_row = (uint32_t)row * 64u;
         const uint32_t sw_x = (uint32_t)((row >> 1) & 3);  // 64-byte swizzle: chunk c of row r sits at c ^ ((r>>1)&3)
         const bool tracer = TRACE && quarter == 0 && lane == 0;
+        const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
 
         float wsc[kScaleDepth][2];
         auto fetch = [&](int j, int t) {
@@ -344,7 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ptx::tmem_wait_st();
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&full[s]);
+                    if (lane == 0) {
+                        // "this warp's 32 rows of A slot s are in TMEM": the payload is tensor memory, completed by
+                        // wait::st above -- no generic-proxy data to release, hence the relaxed remote arrive
+                        if (leader)
+                            ptx::mbar_arrive(&full[s]);
+                        else
+                            ptx::mbar_arrive_cluster_relaxed(lead_full0 + 8u * s);
+                    }
                     if (tracer) trace_ev<TRACE>(p, 6, i);
                 }
             }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::tc_fence_after();
         if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0);
 
-        // this warp: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4)
+        // this warp: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4) (= tokens)
         constexpr int kColsPerWarp = MT / 4;  // 32, 64 or 96
         const int col0 = grp * kColsPerWarp;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
@@ -363,29 +366,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         float bias_v = 0.f;
         if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
 
-        if (splits == 1) {
-#pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
-                uint32_t v[32];
-                ptx::tmem_ld_x32(lane_addr + col0 + c, v);
-                ptx::tmem_wait_ld();
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    const int m = m0 + col0 + c + t;
-                    if (n_ok && m < p.M) {
-                        const T val = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
-                        const long long idx = (long long)m * p.ldc + n;
-                        outp[idx] = val;
-                        for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
-                    }
-                }
-            }
-        } else {
-            // ---- split K: publish the fp32 partial tile ([column][row]: coalesced both ways), count in on the
-            // (tile, CTA) counter; the LAST split to arrive sums all partials in split order.  No CTA waits
-            // for another one.
+        bool finish = true;            // this CTA writes the output tile (false: first split to arrive)
+        const float* other = nullptr;  // the other split's fp32 partial ([column][row]) to add, or NULL
+        if (splits == 2) {
+            // ---- split K: publish the fp32 partial tile ([column][row]: coalesced both ways) and count in on the
+            // (tile, CTA) counter.  The LAST of the two splits to arrive adds the other's partial to its own
+            // accumulators (still in TMEM) and writes the tile; the first one is done.  Nobody waits.
             const int tt = (tile - p.tiles_main) * 2 + (int)cta_rank;
-            float* ws_tile = p.ws_partial + (long long)tt * splits * (kTileN * MT);
+            float* ws_tile = p.ws_partial + (long long)tt * 2 * (kTileN * MT);
             float* my = ws_tile + (long long)split * (kTileN * MT);
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += 32) {
@@ -400,22 +388,59 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (threadIdx.x == 64) {
                 const int old = atomicAdd(p.ws_counter + tt, 1);
                 *s_flag = old;
-                if (old == splits - 1) p.ws_counter[tt] = 0;  // everyone has arrived: reset for the next launch
+                if (old == 1) p.ws_counter[tt] = 0;  // both have arrived: reset for the next launch
                 __threadfence();
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (*s_flag == splits - 1) {
-                for (int c = 0; c < kColsPerWarp; ++c) {
-                    const int m = m0 + col0 + c;
-                    if (m >= p.M) break;
-                    float acc = 0.f;
-                    for (int sp = 0; sp < splits; ++sp)
-                        acc += __ldcg(ws_tile + ((long long)sp * MT + col0 + c) * kTileN + row);
-                    if (n_ok) {
-                        const T val = DT<T>::from_f32(acc + bias_v);
-                        const long long idx = (long long)m * p.ldc + n;
-                        outp[idx] = val;
-                        for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+            finish = *s_flag == 1;
+            other = ws_tile + (long long)(split ^ 1) * (kTileN * MT);
+        }
+
+        if (finish) {
+            if (p.tma_out) {
+                // tile in shared memory: [MT token rows][128 features] of T, 256 B per row, in the idle activation ring
+                T* tile = reinterpret_cast<T*>(sx);
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        float f = __uint_as_float(v[t]);
+                        if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);
+                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(f + bias_v);
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                if (tracer && grp == 0) trace_ev<TRACE>(p, 7, 0);
+                if (quarter == 2 && lane == 0) {  // warp 2 + 4 grp (the first warp of the group)
+                    if (m0 + col0 < p.M) {
+                        for (int d = 0; d <= p.n_peers; ++d)
+                            ptx::tma_store_2d(&omaps.m[d], tile + col0 * kTileN, n0, m0 + col0);
+                        ptx::tma_store_commit();
+                    }
+                    ptx::tma_store_wait_read();  // shared memory must outlive the reads (not the global writes)
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        const int m = m0 + col0 + c + t;
+                        if (n_ok && m < p.M) {
+                            float f = __uint_as_float(v[t]);
+                            if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);
+                            const T val = DT<T>::from_f32(f + bias_v);
+                            const long long idx = (long long)m * p.ldc + n;
+                            outp[idx] = val;
+                            for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                        }
                     }
                 }
             }
@@ -516,6 +541,20 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     if (!cached_tmap(&tmap_w, p.B, 1, 64, (uint64_t)p.N, (uint64_t)p.K / 2, (uint64_t)p.K / 2, (uint32_t)kTileN, 64u))
         return false;
 
+    // output tiles leave through TMA stores when the destination rows are 16-byte aligned
+    OutMaps omaps{};
+    p.tma_out = 0;
+    {
+        bool ok = (p.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+        for (int r = 0; r < p.n_peers; ++r) ok = ok && (reinterpret_cast<uintptr_t>(p.peer_out[r]) & 15) == 0;
+        if (ok) {
+            for (int d = 0; d <= p.n_peers && ok; ++d)
+                ok = encode_tmap_2d(&omaps.m[d], d == 0 ? p.out : p.peer_out[d - 1], 2, 0, (uint64_t)p.M, (uint64_t)p.N,
+                                    (uint64_t)p.ldc * 2, (uint32_t)(MT / 4), (uint32_t)kTileN);
+            p.tma_out = ok ? 1 : 0;
+        }
+    }
+
     p.n_pairs = (p.N + 2 * kTileN - 1) / (2 * kTileN);
     const int m_tiles = (p.M + MT - 1) / MT;
     const int tiles = p.n_pairs * m_tiles;
@@ -528,7 +567,7 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     const int min_stages = force_splits > 0 ? 2 : 8;
     const int max_by_k = p.ka_total / min_stages > 0 ? p.ka_total / min_stages : 1;
     auto clamp = [&](int v) {
-        if (v > 4) v = 4;
+        if (v > 2) v = 2;  // two-way only: the last arriver adds ONE partial to its own accumulators
         if (v > max_by_k) v = max_by_k;
         if (v < 1) v = 1;
         // no empty split: per = ceil(ka/v) rounded up to even
@@ -559,10 +598,8 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     if (split_tiles > 0) {
         Gemm4Workspace ws{};
         if (!gemm4_get_workspace(stream, size_t(split_tiles) * 2 * splits * kTileN * MT * sizeof(float),
-                                 size_t(split_tiles) * 2, &ws)) {
-            set_last_error_msg("gemm4_pair: could not allocate the split-K workspace");
-            return false;
-        }
+                                 size_t(split_tiles) * 2, &ws))
+            return false;  // more split tiles than the fixed workspace holds (forced splits in tests): not served
         p.ws_partial = ws.partial;
         p.ws_counter = ws.counters;
     }
@@ -574,7 +611,7 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_x, tmap_w, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_x, tmap_w, omaps, p);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_last_error("gemm4_pair launch", e);
@@ -610,7 +647,7 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
             const int tiles = n_pairs * ((M + mt - 1) / mt);
             const int rem = tiles % P;
             double rounds = tiles / P;
-            if (rem > 0) rounds += (rem * 2 <= P) ? 1.0 / (P / rem > 4 ? 4 : P / rem) + 0.08 : 1.0;
+            if (rem > 0) rounds += (rem * 2 <= P) ? 0.5 + 0.08 : 1.0;
             return rounds * ((K / 64) * stage_cycles + 3000.0 + 8.0 * mt);
         };
         MT = cost(384, 800.0) <= cost(256, 620.0) ? 384 : 256;

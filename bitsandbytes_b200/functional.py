@@ -130,10 +130,25 @@ def create_fp8_map(signed: bool = True, exponent_bits: int = 5, precision_bits: 
     return code / code.max()
 
 
+_4BIT_CODE_CACHE: dict = {}
+
+
 def get_4bit_type(typename: str, device=None, blocksize: int = 64) -> Tensor:
-    """16 fp32 code values, normalised to max |v| == 1 (reference functional.py:772-859)."""
+    """16 fp32 code values, normalised to max |v| == 1 (reference functional.py:772-859).
+    The device copy is built once per (type, device) and cloned afterwards: a host -> device transfer on every
+    quantize_4bit call would put a synchronising copy on the hot path and break CUDA-graph capture."""
     if device is None:
         device = "cuda"
+    key = (typename, str(torch.device(device)), blocksize)
+    hit = _4BIT_CODE_CACHE.get(key)
+    if hit is not None:
+        return hit.clone()
+    t = _build_4bit_type(typename, device, blocksize)
+    _4BIT_CODE_CACHE[key] = t
+    return t.clone()
+
+
+def _build_4bit_type(typename: str, device, blocksize: int) -> Tensor:
     if typename == "nf4":
         data = list(_NF4_VALUES)
     elif typename == "fp4":

@@ -17,26 +17,32 @@ _ref = None
 
 
 def ref_cuda():
-    """The reference CUDA library (same C ABI), or None if it was not built / cannot load."""
+    """The reference CUDA library (same C ABI, built by oracle/Makefile from the reference sources): the STRICT
+    oracle of the GPU tests.  Not built -> the calling test is skipped, visibly, in the pytest summary; built but
+    not loadable -> the calling test FAILS (a silent downgrade to the looser CPU-oracle bounds is not allowed)."""
+    import pytest
+
     global _ref
     if _ref is None:
         path = oracle.ref_cuda_library_path()
-        if not path.exists():
+        if path is None or not path.exists():
             _ref = False
         else:
             try:
                 dll = ct.CDLL(str(path))
-                for name, (argtypes, restype) in cextension._signatures().items():
-                    if name.startswith("cbnb_b200"):
-                        continue
-                    fn = getattr(dll, name, None)
-                    if fn is not None:
-                        fn.argtypes = argtypes
-                        fn.restype = restype
-                _ref = dll
-            except OSError:
-                _ref = False
-    return _ref or None
+            except OSError as e:
+                pytest.fail(f"the reference CUDA library exists at {path} but does not load: {e}")
+            for name, (argtypes, restype) in cextension._signatures().items():
+                if name.startswith("cbnb_b200"):
+                    continue
+                fn = getattr(dll, name, None)
+                if fn is not None:
+                    fn.argtypes = argtypes
+                    fn.restype = restype
+            _ref = dll
+    if _ref is False:
+        pytest.skip("reference CUDA library not built (oracle/_ref/libbitsandbytes_cuda_ref.so): strict parity not checked")
+    return _ref
 
 
 def stream():

@@ -52,12 +52,14 @@ def eq():
         a = run(L, p)
         nat.check()
         for mt in (128, 256, 384):
-            for sp in (0, 2, 3, 4, 102):
+            for sp in (0, 2, 102):
                 b = run_pair(p, mt, sp)
                 nat.check()
                 if b is None:
-                    print(f"eq {M}x{N}x{K} {qt} {dt} {kw} mt={mt} splits={sp}: NOT SERVED", flush=True)
-                    ok = False
+                    # forcing a split of EVERY tile of a large problem exceeds the fixed split-K workspace
+                    print(f"eq {M}x{N}x{K} {qt} {dt} {kw} mt={mt} splits={sp}: not served"
+                          f"{'' if sp == 2 else ' (UNEXPECTED)'}", flush=True)
+                    ok &= sp == 2
                     continue
                 bad = int((a.view(torch.int16) != b.view(torch.int16)).sum())
                 # split K changes the fp32 summation order: compare within a few ulp instead of bit-equal
@@ -72,9 +74,9 @@ def eq():
                           f"({bad} of {a.numel()})", flush=True)
                     ok &= bad == 0
         # determinism of the split path
-        b1 = run_pair(p, 256, 3)
-        b2 = run_pair(p, 256, 3)
-        same = bool((b1.view(torch.int16) == b2.view(torch.int16)).all())
+        b1 = run_pair(p, 256, 102)
+        b2 = run_pair(p, 256, 102)
+        same = b1 is not None and bool((b1.view(torch.int16) == b2.view(torch.int16)).all())
         print(f"   split determinism: {'OK' if same else 'MISMATCH'}", flush=True)
         ok &= same
     print("eq done ok=", ok, flush=True)
@@ -100,7 +102,7 @@ def time_shapes(shapes):
         nat.check()
 
 
-ROLES = ["x_issue", "mma_full", "mma_issued", "dec_cfull", "dec_math", "dec_empty", "dec_arrived", "relay", "epi_begin", "epi_end"]
+ROLES = ["x_issue", "mma_full", "mma_issued", "dec_cfull", "dec_math", "dec_empty", "dec_arrived", "epi_tile", "epi_begin", "epi_end"]
 
 
 def trace(shape, mt):
@@ -115,10 +117,10 @@ def trace(shape, mt):
     for cta in (0, 1):
         base = t[cta][t[cta] > 0].min()
         print(f"--- trace {M}x{N}x{K} mt={mt} cta {cta} (cycles since first event; per a-stage)")
-        print("  i " + " ".join(f"{r:>11s}" for r in ROLES[:8]))
+        print("  i " + " ".join(f"{r:>11s}" for r in ROLES[:7]))
         for i in list(range(0, min(nst, 24))) + list(range(max(24, nst - 6), nst)):
-            print(f"{i:3d} " + " ".join(f"{(t[cta][r][i] - base) if t[cta][r][i] else -1:11d}" for r in range(8)))
-        print(f"  epilogue begin {t[cta][8][0]-base}, end {t[cta][9][0]-base}")
+            print(f"{i:3d} " + " ".join(f"{(t[cta][r][i] - base) if t[cta][r][i] else -1:11d}" for r in range(7)))
+        print(f"  epilogue begin {t[cta][8][0]-base}, tile in smem {t[cta][7][0]-base}, end {t[cta][9][0]-base}")
         if cta == 0:
             full = t[0][1][:nst].astype(np.int64)
             d = np.diff(full)

@@ -74,6 +74,11 @@ def _signatures():
     sig["cbnb_b200_int8_zero_columns"] = ([_VOIDP] * 2 + [_I32] * 3 + [_VOIDP], None)
     # (A, out, rowStats, col_flags, threshold, rows, cols, dtype, stream)
     sig["cbnb_b200_int8_vector_quant_flags"] = ([_VOIDP] * 4 + [ct.c_float] + [_I32] * 3 + [_VOIDP], None)
+    # (A, B, value, n)
+    sig["cfill_fp32"] = ([_VOIDP, _VOIDP, ct.c_float, ct.c_long], None)
+    sig["cfill_uint8"] = ([_VOIDP, _VOIDP, ct.c_ubyte, ct.c_long], None)
+    sig["carange_fp32"] = ([_VOIDP, _VOIDP, ct.c_float, ct.c_long], None)
+    sig["c_mul_fp32"] = ([_VOIDP, _VOIDP, ct.c_float, ct.c_long], None)
     sig["cget_managed_ptr"] = ([ct.c_size_t], _VOIDP)
     sig["cprefetch"] = ([_VOIDP, ct.c_size_t, _I32], None)
     return sig

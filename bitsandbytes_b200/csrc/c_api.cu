@@ -52,6 +52,8 @@ void launch_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB,
                               int M, int N, int K, int dtype, void* subA, void* subBT, cudaStream_t stream);
 void launch_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream);
 
+template <typename T, int FUNC> void launch_elementwise(T* A, const T* B, T value, long n);
+
 // ---------------------------------------------------------------- error plumbing
 namespace {
 std::mutex g_err_mu;
@@ -486,6 +488,14 @@ void* cget_managed_ptr(size_t bytes) {
     }
     return ptr;
 }
+
+// reference csrc/pythonInterface.cpp:586-592 (A[i] = value / A[i] = i / A[i] *= B[i]; legacy default stream)
+void cfill_fp32(float* A, float* B, float value, long n) { launch_elementwise<float, 0>(A, B, value, n); }
+void cfill_uint8(unsigned char* A, unsigned char* B, unsigned char value, long n) {
+    launch_elementwise<unsigned char, 0>(A, B, value, n);
+}
+void carange_fp32(float* A, float* B, float value, long n) { launch_elementwise<float, 1>(A, B, value, n); }
+void c_mul_fp32(float* A, float* B, float value, long n) { launch_elementwise<float, 2>(A, B, value, n); }
 
 void cprefetch(void* ptr, size_t bytes, int device) {
     int ok = 0;

@@ -60,7 +60,7 @@ constexpr int kTileN = 128;        // features per CTA (TMEM lanes); the pair ow
 constexpr int kAK = 64;            // a-stage: k-elements per TMEM A slot (32 columns)
 constexpr int kCK = 128;           // code stage: k-elements per TMA box of packed codes (64 B per row)
 constexpr int kCodeStageBytes = kTileN * (kCK / 2);  // 8 KB
-constexpr int kNC = 8;             // code ring depth
+constexpr int kNC = 6;             // code ring depth (12 a-stages of run-ahead for the decode warps)
 constexpr int kDecodeWarps = 16;   // 4 groups x 4 warps
 constexpr int kThreads = 32 * (2 + kDecodeWarps + 1);
 constexpr int kScaleDepth = 4;     // per-thread register ring of scales (stages of one group)
@@ -106,9 +106,15 @@ template <int MT> struct PairCfg {
     static constexpr int kBoxRows = kUmmaN / 2;              // token rows this CTA stages per MMA
     static constexpr int kSubBytes = kBoxRows * 128;         // one [kBoxRows x 64] bf16 box, 128-byte swizzle
     static constexpr int kXStageBytes = kNSub * kSubBytes;   // MT/2 tokens x 128 B
-    static constexpr int kNA = (512 - MT) / 32 > 8 ? 8 : (512 - MT) / 32;  // a-stage ring depth: 4 (MT=384) or 8
+    static constexpr int kNA = (512 - MT) / 32 > 8 ? 8 : (512 - MT) / 32;  // TMEM A-slot ring depth: 4 (MT=384) or 8
+    // activation ring (shared memory), decoupled from the A ring: as deep as the budget allows, because the
+    // L2 -> SM path answers a tile load only after ~3000 cycles under load (measured) and the bytes in flight
+    // per SM set the ingest rate
+    static constexpr int kNX = MT == 384 ? 6 : (MT == 256 ? 9 : 12);
     static constexpr uint32_t kACol0 = MT;                   // D: [0, MT); A slot s: MT + 32 s
-    static constexpr size_t kSmemBytes = 1024 + size_t(kNA) * kXStageBytes + size_t(kNC) * kCodeStageBytes + 512;
+    static constexpr size_t kSmemBytes = 1024 + size_t(kNX) * kXStageBytes + size_t(kNC) * kCodeStageBytes + 1024;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(size_t(kNX) * kXStageBytes >= size_t(MT) * 256, "the output tile is staged in the activation ring");
     static_assert(kSubBytes % 1024 == 0, "128-byte swizzle atoms");
 };
 
@@ -119,23 +125,29 @@ template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams&
     }
 }
 
-template <typename T, int QT, int MT, bool TRACE>
+// XLOCAL: every CTA's activation bytes complete on its OWN barrier and the peer forwards one (relaxed) arrive per
+// stage to the leader, instead of the cta_group::2 TMA form whose complete_tx crosses to the leader's barrier.
+template <typename T, int QT, int MT, bool TRACE, bool XLOCAL>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ OutMaps omaps, const PairParams p) {
     using Cfg = PairCfg<MT>;
     constexpr int kNA = Cfg::kNA;
+    constexpr int kNX = Cfg::kNX;
     constexpr int kXStageBytes = Cfg::kXStageBytes;
     constexpr uint32_t kACol0 = Cfg::kACol0;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sx = smem;                                   // [kNA][kNSub][kBoxRows x 128 B]
-    uint8_t* sw = smem + kNA * kXStageBytes;              // [kNC][128 x 64 B]
+    uint8_t* sx = smem;                                   // [kNX][kNSub][kBoxRows x 128 B]
+    uint8_t* sw = smem + kNX * kXStageBytes;              // [kNC][128 x 64 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sw + kNC * kCodeStageBytes);
-    uint64_t* full = bars;                  // [kNA]
-    uint64_t* empty = bars + kNA;           // [kNA]
-    uint64_t* c_full = bars + 2 * kNA;      // [kNC]
+    uint64_t* full = bars;                  // [kNA]  decode warps of both CTAs -> MMA   (leader's is used)
+    uint64_t* empty = bars + kNA;           // [kNA]  MMA -> decode warps (A slot free)
+    uint64_t* x_full = empty + kNA;         // [kNX]  activation bytes -> MMA            (leader's is used)
+    uint64_t* x_empty = x_full + kNX;       // [kNX]  MMA -> activation producer
+    uint64_t* x_local = x_empty + kNX;      // [kNX]  XLOCAL, peer: own bytes landed -> forwarder
+    uint64_t* c_full = x_local + kNX;       // [kNC]
     uint64_t* c_empty = c_full + kNC;       // [kNC]
     uint64_t* acc_full = c_empty + kNC;     // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -171,9 +183,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kNA; ++s) {
-            // leader: producer's expect_tx arrival + the 4 decode warps of each CTA (the peer's never used)
-            ptx::mbar_init(&full[s], 9);
+            ptx::mbar_init(&full[s], 8);  // the 4 decode warps of each CTA (leader's barrier; the peer's is unused)
             ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < kNX; ++s) {
+            // cta_group::2 loads: the leader's producer arms the bytes of both CTAs (1 arrival);
+            // XLOCAL: its own bytes (1 arrival) + the peer's forwarded "my bytes have landed" (1 arrival)
+            ptx::mbar_init(&x_full[s], XLOCAL ? 2 : 1);
+            ptx::mbar_init(&x_empty[s], 1);
+            ptx::mbar_init(&x_local[s], 1);
         }
         for (int s = 0; s < kNC; ++s) {
             ptx::mbar_init(&c_full[s], 1);
@@ -194,20 +212,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 0) {
         // ================================================================== activation producer
         if (lane == 0) {
-            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+            const uint32_t lead_xfull0 = ptx::mapa_u32(ptx::smem_u32(&x_full[0]), 0);
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, i);
+                ptx::mbar_wait_bounded(&x_empty[s], ph ^ 1u, 1, i);
                 trace_ev<TRACE>(p, 0, i);
                 const int k0 = (st_begin + i) * kAK;
-                if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * kXStageBytes);
                 uint8_t* dst = sx + s * kXStageBytes;
+                if constexpr (XLOCAL) {
+                    uint64_t* bar = leader ? &x_full[s] : &x_local[s];
+                    ptx::mbar_arrive_expect_tx(bar, kXStageBytes);
 #pragma unroll
-                for (int sub = 0; sub < Cfg::kNSub; ++sub)
-                    ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_full0 + 8u * s, k0,
-                                          m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
-                if (++s == kNA) {
+                    for (int sub = 0; sub < Cfg::kNSub; ++sub)
+                        ptx::tma_load_2d(dst + sub * Cfg::kSubBytes, &tmap_x, bar, k0,
+                                         m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
+                } else {
+                    if (leader) ptx::mbar_arrive_expect_tx(&x_full[s], 2 * kXStageBytes);
+#pragma unroll
+                    for (int sub = 0; sub < Cfg::kNSub; ++sub)
+                        ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_xfull0 + 8u * s, k0,
+                                              m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
+                }
+                if (++s == kNX) {
                     s = 0;
                     ph ^= 1u;
                 }
@@ -231,30 +258,52 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        int s = 0;
-        uint32_t ph = 0;
-        if (leader) {
+        if (!leader) {
+            if constexpr (XLOCAL) {
+                // ========================================================== forwarder (peer CTA)
+                // "my half of activation stage xs is in my shared memory": one relaxed cluster-scope arrive on
+                // the leader's barrier (the payload was written by the async proxy and is read by the tensor core
+                // after the MMA thread's own acquire of that barrier: nothing for a release fence to publish)
+                const uint32_t lead_xfull0 = ptx::mapa_u32(ptx::smem_u32(&x_full[0]), 0);
+                int xs = 0;
+                uint32_t xph = 0;
+                for (int i = 0; i < nst; ++i) {
+                    ptx::mbar_wait_bounded(&x_local[xs], xph, 3, i);
+                    if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_xfull0 + 8u * xs);
+                    __syncwarp();
+                    if (++xs == kNX) {
+                        xs = 0;
+                        xph ^= 1u;
+                    }
+                }
+            }
+        } else {
             // ============================================================== MMA issuer (leader CTA)
             constexpr uint32_t idesc =
                 ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
+            int s = 0, xs = 0;
+            uint32_t ph = 0, xph = 0;
             for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&full[s], ph, 4, i);
+                ptx::mbar_wait_bounded(&x_full[xs], xph, 4, i);
+                if (lane == 0) trace_ev<TRACE>(p, 1, i);
+                ptx::mbar_wait_bounded(&full[s], ph, 8, i);
                 ptx::tc_fence_after();
                 if (lane == 0) {
-                    trace_ev<TRACE>(p, 1, i);
-                    const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
+                    trace_ev<TRACE>(p, 7, i);
+                    const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
                     const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
 #pragma unroll
                     for (int k = 0; k < kAK / 16; ++k) {
 #pragma unroll
                         for (int sub = 0; sub < Cfg::kNSub; ++sub) {
                             // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
-                            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xs + sub * Cfg::kSubBytes) + 2 * k;
+                            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
                             ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
                                                  (i | k) != 0 ? 1u : 0u);
                         }
                     }
                     ptx::tc_commit_pair(&empty[s], 0x3);
+                    ptx::tc_commit_pair(&x_empty[xs], 0x3);
                     if (i == nst - 1) ptx::tc_commit_pair(acc_full, 0x3);
                     trace_ev<TRACE>(p, 2, i);
                 }
@@ -262,6 +311,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (++s == kNA) {
                     s = 0;
                     ph ^= 1u;
+                }
+                if (++xs == kNX) {
+                    xs = 0;
+                    xph ^= 1u;
                 }
             }
         }
@@ -415,7 +468,6 @@ __global__ void __launch_bounds__(kThreads, 1)
                 ptx::fence_proxy_async_smem();
                 // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-                if (tracer && grp == 0) trace_ev<TRACE>(p, 7, 0);
                 if (quarter == 2 && lane == 0) {  // warp 2 + 4 grp (the first warp of the group)
                     if (m0 + col0 < p.M) {
                         for (int d = 0; d <= p.n_peers; ++d)
@@ -497,10 +549,10 @@ bool cached_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle
     return true;
 }
 
-template <typename T, int QT, int MT, bool TRACE>
+template <typename T, int QT, int MT, bool TRACE, bool XLOCAL>
 bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_splits) {
     using Cfg = PairCfg<MT>;
-    auto kern = gemm4_pair_kernel<T, QT, MT, TRACE>;
+    auto kern = gemm4_pair_kernel<T, QT, MT, TRACE, XLOCAL>;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};  // the opt-in is per device
@@ -672,11 +724,21 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
     p.log2_bs = ilog2_pow2(blocksize);
     p.ka_total = K / kAK;
 
+    // A/B switch (read per call so that one process can compare): BNB_B200_PAIR_XLOCAL=1 -> per-CTA activation
+    // barriers + forwarded arrive instead of cta_group::2 TMA loads completing on the leader's barrier
+    const char* xl = getenv("BNB_B200_PAIR_XLOCAL");
+    const bool xlocal = xl != nullptr && xl[0] == '1';
 #define BNB200_PAIR_MT(QT, TR)                                                                                         \
     switch (MT) {                                                                                                      \
-    case 128: return launch_pair_mt<T, QT, 128, TR>(A, p, stream, force_splits);                                       \
-    case 256: return launch_pair_mt<T, QT, 256, TR>(A, p, stream, force_splits);                                       \
-    default: return launch_pair_mt<T, QT, 384, TR>(A, p, stream, force_splits);                                        \
+    case 128:                                                                                                          \
+        return xlocal ? launch_pair_mt<T, QT, 128, TR, true>(A, p, stream, force_splits)                               \
+                      : launch_pair_mt<T, QT, 128, TR, false>(A, p, stream, force_splits);                             \
+    case 256:                                                                                                          \
+        return xlocal ? launch_pair_mt<T, QT, 256, TR, true>(A, p, stream, force_splits)                               \
+                      : launch_pair_mt<T, QT, 256, TR, false>(A, p, stream, force_splits);                             \
+    default:                                                                                                           \
+        return xlocal ? launch_pair_mt<T, QT, 384, TR, true>(A, p, stream, force_splits)                               \
+                      : launch_pair_mt<T, QT, 384, TR, false>(A, p, stream, force_splits);                             \
     }
     if (trace != nullptr) {
         if (quant_type == kNF4) {

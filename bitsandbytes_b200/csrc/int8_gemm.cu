@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     float* s_scb = reinterpret_cast<float*>(smem + kI8Stages * kI8StageBytes);   // [2][256]
     float* s_bias = s_scb + 2 * kI8TileN;                                          // [2][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kI8Stages * kI8StageBytes + 4096);
+    // outlier weights of 128 output features at a time: [128][JMAX] of T (row = feature), after the barriers
+    uint4* s_sub = reinterpret_cast<uint4*>(smem + kI8Stages * kI8StageBytes + 4096 + 256);
     uint64_t* full = bars;                       // [stages] TMA -> MMA
     uint64_t* empty = bars + kI8Stages;          // [stages] MMA of both cluster CTAs -> TMA
     uint64_t* tmem_full = bars + 2 * kI8Stages;  // [2] MMA -> epilogue
@@ -270,22 +272,19 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                     for (int e = 0; e < 8; ++e) oa[8 * g + e] = t8[e];
                 }
             }
-            // outlier term of output feature n for this token: sum_j subA[m, j] * subBT[n, j]
-            // (every lane of the warp reads the same subBT row: one broadcast sector per load, L1-resident)
-            auto outlier = [&](int n) -> float {
+            // outlier term of tile column cc for this token: sum_j subA[m, j] * subBT[n0 + cc, j], the weights read from
+            // the staged half tile (every lane reads the same row: shared-memory broadcast, no bank conflicts)
+            auto outlier = [&](int cc) -> float {
                 float o = 0.f;
                 if constexpr (JMAX > 0) {
-                    if (n < p.N) {
-                        const uint4* brow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.subBT) +
-                                                                           (long long)n * p.jpad);
+                    const uint4* brow = s_sub + (cc & 127) * (JMAX / 8);
 #pragma unroll
-                        for (int g = 0; g < JMAX / 8; ++g) {
-                            if (8 * g < p.jpad) {
-                                float b8[8];
-                                i8_unpack8<EPI>(__ldg(brow + g), b8);
+                    for (int g = 0; g < JMAX / 8; ++g) {
+                        if (8 * g < p.jpad) {
+                            float b8[8];
+                            i8_unpack8<EPI>(brow[g], b8);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) o = fmaf(oa[8 * g + e], b8[e], o);
-                            }
+                            for (int e = 0; e < 8; ++e) o = fmaf(oa[8 * g + e], b8[e], o);
                         }
                     }
                 }
@@ -296,6 +295,22 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * kI8TileN;
 #pragma unroll 1
             for (int c = 0; c < kI8TileN; c += 32) {
+                if constexpr (JMAX > 0) {
+                    if ((c & 127) == 0) {
+                        // stage subBT[n0 + c .. + 128) (zero rows past N): thread et owns feature row et
+                        asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous half has been consumed
+                        const int nn = n0 + c + et;
+#pragma unroll
+                        for (int g = 0; g < JMAX / 8; ++g) {
+                            uint4 r = make_uint4(0, 0, 0, 0);
+                            if (nn < p.N && 8 * g < p.jpad)
+                                r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.subBT) +
+                                                                         (long long)nn * p.jpad + 8 * g));
+                            s_sub[et * (JMAX / 8) + g] = r;
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                }
                 uint32_t v[32];
                 ptx::tmem_ld_x32(lane_addr + c, v);
                 ptx::tmem_wait_ld();
@@ -332,8 +347,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                             if constexpr (JMAX > 0) {
                                 // reference: the int8 result is an fp16 tensor, then addmm adds the fp32-accumulated
                                 // outlier product and rounds once more
-                                f0 = __half2float(__float2half_rn(f0)) + outlier(n + t);
-                                f1 = __half2float(__float2half_rn(f1)) + outlier(n + t + 1);
+                                f0 = __half2float(__float2half_rn(f0)) + outlier(c + t);
+                                f1 = __half2float(__float2half_rn(f1)) + outlier(c + t + 1);
                             }
                             w[t >> 1] = pack2<__half>(f0, f1);
                         } else {
@@ -348,8 +363,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                                 f1 = __half2float(__float2half_rn(f1 + sbias[c + t + 1]));
                             }
                             if constexpr (JMAX > 0) {
-                                f0 = __bfloat162float(__float2bfloat16_rn(f0)) + outlier(n + t);
-                                f1 = __bfloat162float(__float2bfloat16_rn(f1)) + outlier(n + t + 1);
+                                f0 = __bfloat162float(__float2bfloat16_rn(f0)) + outlier(c + t);
+                                f1 = __bfloat162float(__float2bfloat16_rn(f1)) + outlier(c + t + 1);
                             }
                             w[t >> 1] = pack2<__nv_bfloat16>(f0, f1);
                         }
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 template <int EPI, bool PAIR, int KSUB, int JMAX = 0>
 int launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params& p, cudaStream_t stream) {
     using Cfg = I8Cfg<PAIR, KSUB>;
-    constexpr size_t smem_bytes = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + 4096 + 256;
+    constexpr size_t smem_bytes = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + 4096 + 256 + size_t(128) * JMAX * 2;
     static bool attr_set[64] = {};  // the shared-memory opt-in is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;

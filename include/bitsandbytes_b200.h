@@ -117,6 +117,15 @@ void cdequant_mm_int32_fp16(int* A, float* rowStats, float* colStats, bnb_half* 
  * Replaces reference csrc/pythonInterface.cpp:551-555; kernel csrc/kernels.cu:1331-1385. */
 void cint8_vector_quant(bnb_half* A, int8_t* out, float* rowStats, float threshold, int rows, int cols, bnb_stream_t stream);
 
+/* Element-wise helpers of the reference's paged-memory utilities: A[i] = value, A[i] = i, A[i] *= B[i]
+ * (legacy default stream, as in the reference).  Outside the hot path; present so that the reference's loader and
+ * its functional.fill / arange / _mul helpers find them.
+ * Replaces reference csrc/pythonInterface.cpp:586-592; kernel csrc/kernels.cu:1569-1583. */
+void cfill_fp32(float* A, float* B, float value, long n);
+void cfill_uint8(unsigned char* A, unsigned char* B, unsigned char value, long n);
+void carange_fp32(float* A, float* B, float value, long n);
+void c_mul_fp32(float* A, float* B, float value, long n);
+
 /* =====================================================================
  * 2. B200-native additions (no reference counterpart)
  * ===================================================================== */

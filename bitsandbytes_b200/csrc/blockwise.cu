@@ -79,6 +79,82 @@ __device__ __forceinline__ unsigned quantize_fp4(float x) {
     return c + sign;
 }
 
+// The same two decision procedures as ONE table look-up + ONE comparison (the fast kernel's form).
+// Both procedures are "which interval between consecutive pivots holds x" (NF4: 15 pivots on [-1, 1]; FP4: 7 on
+// |x|), and no two pivots are closer than 0.08, so a uniform grid of width 1/16 has at most one pivot per cell:
+//     t = int((x + 1) * 16)  [NF4]   /   int(|x| * 16)  [FP4]          (NaN -> 0, where every comparison is false)
+//     entry t = { the pivot inside cell t (or +inf), code below it | (code below ^ code above) << 8 }
+//     code = below ^ (x > pivot ? (below ^ above) : 0)
+// x is a * rcp(absmax) with |a| <= absmax, so |x| <= 1 + 2^-22 and t stays inside the 33- / 17-entry table.
+// Equality with the trees above for every such fp32 value (and NaN) is proved exhaustively on the CPU
+// (tools/micro/q4_lut_equiv.c); a cell edge is never within rounding distance of a pivot.
+constexpr int kQ4LutNF4 = 33, kQ4LutFP4 = 17;
+
+template <int QT> __device__ __forceinline__ void build_q4_lut(float2* lut, int t) {
+    constexpr float kPivNF4[15] = {-0.8480964004993439f, -0.6106329262256622f, -0.4599952697753906f,
+                                   -0.33967943489551544f, -0.23460740596055984f, -0.13791173323988914f,
+                                   -0.045525018125772476f, 0.03979014977812767f, 0.1202552504837513f,
+                                   0.2035212516784668f, 0.2920137718319893f, 0.3893125355243683f,
+                                   0.5016634166240692f, 0.6427869200706482f, 0.8614784181118011f};
+    constexpr float kPivFP4[7] = {0.00260417f, 0.0859375f, 0.20833333f, 0.29166667f, 0.4166667f, 0.583333f, 0.8333333f};
+    constexpr unsigned kCodeFP4[8] = {0u, 1u, 6u, 7u, 4u, 5u, 2u, 3u};  // code of the interval below pivot i / above the last
+    const float lo = QT == kNF4 ? (float)t * 0.0625f - 1.0f : (float)t * 0.0625f;
+    const float hi = lo + 0.0625f;
+    int r = 0;  // pivots below the cell
+    if (QT == kNF4) {
+#pragma unroll
+        for (int i = 0; i < 15; ++i) r += kPivNF4[i] < lo ? 1 : 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) r += kPivFP4[i] < lo ? 1 : 0;
+    }
+    float pivot = __int_as_float(0x7f800000);
+    unsigned below, above;
+    if (QT == kNF4) {
+        below = (unsigned)r;
+        above = below;
+        if (r < 15) {
+            float pv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 15; ++i) pv = i == r ? kPivNF4[i] : pv;
+            if (pv < hi) {
+                pivot = pv;
+                above = below + 1u;
+            }
+        }
+    } else {
+        unsigned cb = 0u, ca = 0u;
+        float pv = 2.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            cb = i == r ? kCodeFP4[i] : cb;
+            ca = i == r + 1 ? kCodeFP4[i] : ca;
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) pv = i == r ? kPivFP4[i] : pv;
+        below = cb;
+        above = cb;
+        if (r < 7 && pv < hi) {
+            pivot = pv;
+            above = ca;
+        }
+    }
+    lut[t] = make_float2(pivot, __uint_as_float(below | ((below ^ above) << 8)));
+}
+
+template <int QT> __device__ __forceinline__ unsigned quantize4_lut(const float2* __restrict__ lut, float x) {
+    if (QT == kNF4) {
+        const float2 e = lut[__float2int_rz(fmaf(x, 16.0f, 16.0f))];
+        const unsigned w = __float_as_uint(e.y);
+        return (w & 0xffu) ^ ((x > e.x) ? (w >> 8) : 0u);
+    } else {
+        const float a = fabsf(x);
+        const float2 e = lut[__float2int_rz(a * 16.0f)];
+        const unsigned w = __float_as_uint(e.y);
+        return ((w & 0xffu) ^ ((a > e.x) ? (w >> 8) : 0u)) | ((x < 0.0f) ? 8u : 0u);
+    }
+}
+
 // 8-bit dynamic map: reference kernels.cu:160-219 (dQuantize<0>).  Same 7-step search
 // from pivot 127 and the same midpoint rule; the code book lives in shared memory.
 __device__ __forceinline__ unsigned quantize_8bit(const float* __restrict__ scode, float x) {
@@ -159,14 +235,16 @@ template <> struct VecIO<__nv_bfloat16> {
     }
 };
 
-// The same codes with fewer instructions (BNB_B200_Q8_FAST=1; experimental, written at the end of round 1,
-// not yet run on a GPU).  For a sorted code book every comparison of the walk above is decided by
-// c = #{j : code[j] < x}, so the walk's end state -- its last pivot and the neighbour it may still move
-// to -- is a function of c alone: a 257-entry structural table (q8_structure) that does not depend on
-// the code values.  c comes from a 9-probe lower-bound search (3 instructions per probe instead of 8),
-// the final decision is the reference's own midpoint rule.  Equivalence with quantize_8bit is proved
-// exhaustively on the CPU for all 2^32 inputs and six code books, duplicates included
-// (tools/micro/q8_search_equiv.c).
+// The same codes with fewer instructions (the fast kernel's form).  For a sorted code book every comparison of the
+// walk above is decided by c = #{j : code[j] < x}, so the walk's end state -- its last pivot and the neighbour it
+// may still move to -- is a function of c alone: a 257-entry structural table (q8_structure) that does not depend on
+// the code values; the final decision is the reference's own midpoint rule.  (Proved exhaustively on the CPU for all
+// 2^32 inputs and six code books, duplicates included: tools/micro/q8_search_equiv.c.)
+// c itself comes from a BRACKET table instead of a search: the value axis is cut into 772 cells by the float's own
+// bits (sign, exponent, 4 mantissa bits; everything below 2^-24 in one cell per sign), T[t] = #{j : code[j] < low(t)}
+// is built once per CTA (773 nine-probe searches), and for x in cell t   T[t] <= c <= T[t+1],   so a short linear
+// scan (0..3 steps for the default dynamic map) finishes the count.  ~35 instructions per element instead of ~70.
+// Equality with quantize_8bit for every fp32 input the kernel can produce: tools/micro/q8_lut_equiv.c.
 // entry c of the structural table, pre-scaled to byte offsets into the code book:
 // (4 * last pivot) | (4 * neighbour it may still move to) << 16
 __device__ __forceinline__ uint32_t q8_structure(int c) {
@@ -181,26 +259,56 @@ __device__ __forceinline__ uint32_t q8_structure(int c) {
     return (uint32_t)(4 * pivot) | ((uint32_t)(4 * (pivot < c ? up : lp)) << 16);
 }
 
-// all indices are kept as BYTE offsets (c4 = 4 c) so that every probe is one LDS with an immediate,
-// one FSETP and one predicated add
-__device__ __forceinline__ unsigned quantize_8bit_fast(const float* __restrict__ scode,
-                                                       const uint32_t* __restrict__ spo, float x) {
-    const char* cb = reinterpret_cast<const char*>(scode);
-    unsigned c4 = 0;
+constexpr int kQ8MinKey = ((127 - 24) << 4) - 1;         // magnitude keys <= this share cell 0: |x| < 2^-24
+constexpr int kQ8MagCells = (127 << 4) - kQ8MinKey + 1;   // 386: the last one is [1, 1.0625)
+constexpr int kQ8Cells = 2 * kQ8MagCells;                 // negative cells (most negative first), then positive
+
+// lower edge of magnitude cell cm (cm = 0: zero)
+__device__ __forceinline__ float q8_mag_edge(int cm) {
+    return cm == 0 ? 0.0f : __uint_as_float((uint32_t)(cm + kQ8MinKey) << 19);
+}
+
+// bracket entry t: T[t] | T[t + 1] << 16 with T[t] = #{j : code[j] < low(t)}; low(t) = the (exclusive, for negative
+// cells: values (-edge(cm+1), -edge(cm)]) lower end of value cell t; T[kQ8Cells] counts against 1.0625
+__device__ __forceinline__ uint32_t q8_count_below(const float* __restrict__ scode, float v) {
+    unsigned c = 0;
 #pragma unroll
-    for (int s = 128; s > 0; s >>= 1)
-        c4 += (*reinterpret_cast<const float*>(cb + c4 + 4 * (s - 1)) < x) ? 4u * s : 0u;
-    c4 += (c4 == 1020u && scode[255] < x) ? 4u : 0u;
-    const uint32_t po = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(spo) + c4);
+    for (int s = 128; s > 0; s >>= 1) c += (scode[c + s - 1] < v) ? (unsigned)s : 0u;
+    c += (c == 255u && scode[255] < v) ? 1u : 0u;
+    return c;
+}
+__device__ __forceinline__ float q8_cell_low(int t) {
+    if (t < kQ8MagCells) return -q8_mag_edge(kQ8MagCells - t);  // cm = kQ8MagCells - 1 - t, low = -edge(cm + 1)
+    return q8_mag_edge(t - kQ8MagCells);
+}
+__device__ __forceinline__ void build_q8_bracket(const float* __restrict__ scode, uint32_t* __restrict__ sbr) {
+    for (int t = threadIdx.x; t < kQ8Cells; t += blockDim.x)
+        sbr[t] = q8_count_below(scode, q8_cell_low(t)) | (q8_count_below(scode, q8_cell_low(t + 1)) << 16);
+}
+
+__device__ __forceinline__ unsigned quantize_8bit_fast(const float* __restrict__ scode,
+                                                       const uint32_t* __restrict__ spo,
+                                                       const uint32_t* __restrict__ sbr, float x) {
+    // value cell: magnitude key, everything tiny (and NaN, whose key is out of range) -> 0; zero counts as positive
+    unsigned cm = ((__float_as_uint(x) & 0x7fffffffu) >> 19) - (unsigned)kQ8MinKey;
+    cm = cm < (unsigned)kQ8MagCells ? cm : 0u;
+    const unsigned t = (unsigned)kQ8MagCells + ((x < 0.0f) ? ~cm : cm);
+    const uint32_t br = sbr[t];
+    unsigned c = br & 0xffffu;
+    const unsigned hi = br >> 16;
+    while (c < hi && scode[c] < x) ++c;
+    c = (x == x) ? c : 0u;  // NaN (0 * rcp(0)): no entry is below it
+    const uint32_t po = spo[c];
+    const char* cb = reinterpret_cast<const char*>(scode);
     const unsigned p4 = po & 0xffffu, o4 = po >> 16;
     const float midpoint = mul_ftz(*reinterpret_cast<const float*>(cb + o4) + *reinterpret_cast<const float*>(cb + p4), 0.5f);
-    const bool move = (p4 < c4) ? (x > midpoint) : (x < midpoint);
+    const bool move = (p4 < 4u * c) ? (x > midpoint) : (x < midpoint);
     return (move ? o4 : p4) >> 2;
 }
 
 template <int QT>
-__device__ __forceinline__ unsigned quantize_8bit_any(const float* scode, const uint32_t* spo, float x) {
-    return QT == kGeneral8bitFast ? quantize_8bit_fast(scode, spo, x) : quantize_8bit(scode, x);
+__device__ __forceinline__ unsigned quantize_8bit_any(const float* scode, const uint32_t* spo, const uint32_t* sbr, float x) {
+    return QT == kGeneral8bitFast ? quantize_8bit_fast(scode, spo, sbr, x) : quantize_8bit(scode, x);
 }
 
 constexpr int kQThreads = 256;
@@ -216,6 +324,8 @@ __global__ void __launch_bounds__(kQThreads)
     __shared__ float scode[256];
     __shared__ float swarp[kQThreads / 32];
     __shared__ uint32_t spo[QT == kGeneral8bitFast ? 257 : 1];
+    __shared__ uint32_t sbr[QT == kGeneral8bitFast ? kQ8Cells : 1];
+    __shared__ float2 q4lut[QT == kNF4 ? kQ4LutNF4 : (QT == kFP4 ? kQ4LutFP4 : 1)];
     constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;
 
     if (k8) {
@@ -224,6 +334,13 @@ __global__ void __launch_bounds__(kQThreads)
             spo[threadIdx.x] = q8_structure(threadIdx.x);
             if (threadIdx.x == 0) spo[256] = q8_structure(256);
         }
+        __syncthreads();
+        if (QT == kGeneral8bitFast) {
+            build_q8_bracket(scode, sbr);
+            __syncthreads();
+        }
+    } else {
+        if (threadIdx.x < (QT == kNF4 ? kQ4LutNF4 : kQ4LutFP4)) build_q4_lut<QT>(q4lut, threadIdx.x);
         __syncthreads();
     }
 
@@ -270,10 +387,10 @@ __global__ void __launch_bounds__(kQThreads)
                 uint32_t w[VE / 4];
 #pragma unroll
                 for (int q = 0; q < VE / 4; ++q) {
-                    uint32_t b0 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 0], inv));
-                    uint32_t b1 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 1], inv));
-                    uint32_t b2 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 2], inv));
-                    uint32_t b3 = quantize_8bit_any<QT>(scode, spo, mul_ftz(x[v][4 * q + 3], inv));
+                    uint32_t b0 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 0], inv));
+                    uint32_t b1 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 1], inv));
+                    uint32_t b2 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 2], inv));
+                    uint32_t b3 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 3], inv));
                     w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
                 }
                 if (VE == 4)
@@ -285,8 +402,8 @@ __global__ void __launch_bounds__(kQThreads)
 #pragma unroll
                 for (int p = 0; p < VE / 2; ++p) {
                     float x0 = mul_ftz(x[v][2 * p], inv), x1 = mul_ftz(x[v][2 * p + 1], inv);
-                    uint32_t hi = QT == kNF4 ? quantize_nf4(x0) : quantize_fp4(x0);
-                    uint32_t lo = QT == kNF4 ? quantize_nf4(x1) : quantize_fp4(x1);
+                    uint32_t hi = quantize4_lut<QT>(q4lut, x0);
+                    uint32_t lo = quantize4_lut<QT>(q4lut, x1);
                     w |= ((hi << 4) | lo) << (8 * p);
                 }
                 if (VE == 4)
@@ -307,14 +424,9 @@ __global__ void __launch_bounds__(256)
                                       float* __restrict__ absmax, uint8_t* __restrict__ out, int bs,
                                       long long first_block, long long n) {
     __shared__ float scode[256];
-    __shared__ uint32_t spo[QT == kGeneral8bitFast ? 257 : 1];
-    constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;
+    constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;  // the tail always takes the plain walk
     if (k8) {
         scode[threadIdx.x] = code[threadIdx.x];
-        if (QT == kGeneral8bitFast) {
-            spo[threadIdx.x] = q8_structure(threadIdx.x);
-            if (threadIdx.x == 0) spo[256] = q8_structure(256);
-        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -332,7 +444,7 @@ __global__ void __launch_bounds__(256)
         const float inv = rcp_approx_ftz(m);
         if (k8) {
             for (long long i = lo + lane; i < hi; i += 32)
-                out[i] = (uint8_t)quantize_8bit_any<QT>(scode, spo, mul_ftz(DT<T>::to_f32(A[i]), inv));
+                out[i] = (uint8_t)quantize_8bit(scode, mul_ftz(DT<T>::to_f32(A[i]), inv));
         } else {
             // bytes [lo/2, (hi+1)/2): element past the end reads as 0.0f (reference pads with T(0))
             for (long long i = lo + 2 * lane; i < hi; i += 64) {

@@ -149,7 +149,7 @@ static int mma_max_m() {
     if (v == -2) {
         const char* e = getenv("BNB_B200_MMA_MAX_M");
         v = e ? atoi(e) : 8;
-        if (v > 8) v = 8;
+        if (v > 16) v = 16;  // the mma.sync decode kernel serves up to two groups of 8 tokens
     }
     return v;
 }

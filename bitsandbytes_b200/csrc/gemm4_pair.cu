@@ -279,44 +279,70 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         } else {
             // ============================================================== MMA issuer (leader CTA)
-            constexpr uint32_t idesc =
-                ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
-            int s = 0, xs = 0;
-            uint32_t ph = 0, xph = 0;
-            for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&x_full[xs], xph, 4, i);
-                if (lane == 0) trace_ev<TRACE>(p, 1, i);
-                ptx::mbar_wait_bounded(&full[s], ph, 8, i);
-                ptx::tc_fence_after();
-                if (lane == 0) {
-                    trace_ev<TRACE>(p, 7, i);
+            // One thread runs the whole loop.  Measured on B200 (round 2 traces): the tensor core accepts a
+            // tcgen05.mma only about one instruction ahead of the one it executes, so every cycle this thread spends
+            // in an mbarrier wait or a commit BETWEEN stages drains the pipe (two waits + two commits cost ~550 of
+            // 1300 cycles per stage).  The waits for stage i+1 are therefore issued as single non-blocking probes IN
+            // THE MIDDLE of stage i's MMAs -- the operands are ready long before, the probes succeed, and their
+            // latency hides under the MMAs still queued; only a failed probe falls back to a blocking wait.
+            if (lane == 0) {
+                constexpr uint32_t idesc =
+                    ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
+                constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
+                int s = 0, xs = 0;
+                uint32_t ph = 0, xph = 0;
+                ptx::mbar_wait_bounded(&x_full[0], 0, 4, 0);
+                ptx::mbar_wait_bounded(&full[0], 0, 8, 0);
+                for (int i = 0; i < nst; ++i) {
+                    trace_ev<TRACE>(p, 1, i);
+                    ptx::tc_fence_after();
+                    int ns = s + 1, nxs = xs + 1;
+                    uint32_t nph = ph, nxph = xph;
+                    if (ns == kNA) {
+                        ns = 0;
+                        nph ^= 1u;
+                    }
+                    if (nxs == kNX) {
+                        nxs = 0;
+                        nxph ^= 1u;
+                    }
+                    const bool more = i + 1 < nst;
+                    bool okx = false, oka = false;
                     const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
                     const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
+                    // TRACE builds: per-instruction issue times of a-stages 24 and 25 (role 9, entries 1..)
+                    const bool micro = TRACE && (i == 24 || i == 25);
+                    int mslot = 1 + (i - 24) * 16;
+                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
 #pragma unroll
-                    for (int k = 0; k < kAK / 16; ++k) {
-#pragma unroll
-                        for (int sub = 0; sub < Cfg::kNSub; ++sub) {
-                            // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
-                            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
-                            ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
-                                                 (i | k) != 0 ? 1u : 0u);
-                        }
+                    for (int j = 0; j < kMmas; ++j) {
+                        const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
+                        // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
+                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
+                        ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
+                                             (i | k) != 0 ? 1u : 0u);
+                        if (micro) trace_ev<TRACE>(p, 9, mslot++);
+                        if (j == kMmas / 2 - 1 && more) okx = ptx::mbar_try_wait(&x_full[nxs], nxph);
+                        if (j == kMmas - 2 && more) oka = ptx::mbar_try_wait(&full[ns], nph);
                     }
                     ptx::tc_commit_pair(&empty[s], 0x3);
+                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
                     ptx::tc_commit_pair(&x_empty[xs], 0x3);
+                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
                     if (i == nst - 1) ptx::tc_commit_pair(acc_full, 0x3);
                     trace_ev<TRACE>(p, 2, i);
-                }
-                __syncwarp();
-                if (++s == kNA) {
-                    s = 0;
-                    ph ^= 1u;
-                }
-                if (++xs == kNX) {
-                    xs = 0;
-                    xph ^= 1u;
+                    if (more) {
+                        if (!okx) ptx::mbar_wait_bounded(&x_full[nxs], nxph, 4, i + 1);
+                        if (!oka) ptx::mbar_wait_bounded(&full[ns], nph, 8, i + 1);
+                    }
+                    trace_ev<TRACE>(p, 7, i);
+                    s = ns;
+                    ph = nph;
+                    xs = nxs;
+                    xph = nxph;
                 }
             }
+            __syncwarp();
         }
     } else {
         // ================================================================== decode warps

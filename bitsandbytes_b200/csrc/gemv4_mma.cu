@@ -55,12 +55,13 @@ template <> struct WarpMma<__half> {
 // activations come through L1 (every CTA on an SM reads the same M x K slice).  Measured and dropped:
 // staging the activations with cp.async (slower, it bypasses L1), issuing their loads before the
 // decode, 3 or 4 CTAs per SM through a register cap -- all within noise of this version.
-template <typename T, int QT, int W>
+// NT = groups of 8 tokens (1: M <= 8, 2: M <= 16): the decoded weight fragments feed NT MMAs each.
+template <typename T, int QT, int W, int NT>
 __global__ void __launch_bounds__(W * 32, 2)
     gemv4_mma_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, const float* absmax,
                      const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset,
                      T* __restrict__ out, const T* __restrict__ bias, int M, int N, int K, int ldc, int log2_bs) {
-    __shared__ float red[W][kGRows * 8];
+    __shared__ float red[W][kGRows * 8 * NT];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2;
@@ -69,8 +70,13 @@ __global__ void __launch_bounds__(W * 32, 2)
     ScaleSrc sc{absmax, absmax_8bit, absmax_code,
                 (absmax_8bit != nullptr && absmax_offset != nullptr) ? __ldg(absmax_offset) : 0.f};
     const bool two_scales = log2_bs == 5;  // blocksize 32: two quantisation blocks per 64 codes
-    const bool tok_ok = g < M;             // this lane's token (MMA column g)
-    const T* arow = A + (long long)(tok_ok ? g : 0) * K;
+    bool tok_ok[NT];                       // this lane's tokens (MMA column g of token group u)
+    const T* arow[NT];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        tok_ok[u] = g + 8 * u < M;
+        arow[u] = A + (long long)(tok_ok[u] ? g + 8 * u : 0) * K;
+    }
 
     // this lane's two weight rows (rows past N contribute zero fragments)
     long long e_row[2];
@@ -82,7 +88,9 @@ __global__ void __launch_bounds__(W * 32, 2)
         e_row[h] = (long long)(row_ok[h] ? n : 0) * K;
     }
 
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    float c[NT][4];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f;
     const int nchunks = (K + kGChunk - 1) / kGChunk;
 
     uint4 q[2][2];
@@ -112,7 +120,6 @@ __global__ void __launch_bounds__(W * 32, 2)
         const uint4 q00 = q[0][0], q01 = q[0][1], q10 = q[1][0], q11 = q[1][1];
         const float s00 = s[0][0], s01 = s[0][1], s10 = s[1][0], s11 = s[1][1];
         fetch(ch + W);
-        const uint4* xp = reinterpret_cast<const uint4*>(arow + kb);
 
         DecodeTable tab0, tab1;
         build_table<T, QT>(s00, tab0);
@@ -134,33 +141,38 @@ __global__ void __launch_bounds__(W * 32, 2)
             decode_word(qb.y, tab1, rb + 4);
             decode_word(qb.z, tab1, rb + 8);
             decode_word(qb.w, tab1, rb + 12);
-            // activations of token g at the same 32 k: 16 pairs
-            uint32_t xw[16];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                uint4 av = make_uint4(0, 0, 0, 0);
-                if (tok_ok && k_ok) av = __ldg(xp + 4 * hh + v);
-                xw[4 * v + 0] = av.x;
-                xw[4 * v + 1] = av.y;
-                xw[4 * v + 2] = av.z;
-                xw[4 * v + 3] = av.w;
+            for (int u = 0; u < NT; ++u) {
+                // activations of token g + 8u at the same 32 k: 16 pairs
+                const uint4* xp = reinterpret_cast<const uint4*>(arow[u] + kb);
+                uint32_t xw[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 av = make_uint4(0, 0, 0, 0);
+                    if (tok_ok[u] && k_ok) av = __ldg(xp + 4 * hh + v);
+                    xw[4 * v + 0] = av.x;
+                    xw[4 * v + 1] = av.y;
+                    xw[4 * v + 2] = av.z;
+                    xw[4 * v + 3] = av.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    WarpMma<T>::run(c[u], ra[2 * j], rb[2 * j], ra[2 * j + 1], rb[2 * j + 1], xw[2 * j], xw[2 * j + 1]);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                WarpMma<T>::run(c, ra[2 * j], rb[2 * j], ra[2 * j + 1], rb[2 * j + 1], xw[2 * j], xw[2 * j + 1]);
         }
     }
 
-    // accumulator fragment: c0/c1 = (row g, tokens 2t, 2t+1), c2/c3 = (row g + 8, same tokens)
-    {
-        float* r = red[warp];
-        r[(2 * t) * kGRows + g] = c[0];
-        r[(2 * t + 1) * kGRows + g] = c[1];
-        r[(2 * t) * kGRows + g + 8] = c[2];
-        r[(2 * t + 1) * kGRows + g + 8] = c[3];
+    // accumulator fragment: c0/c1 = (row g, tokens 8u + 2t, 8u + 2t+1), c2/c3 = (row g + 8, same tokens)
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        float* r = red[warp] + u * 8 * kGRows;
+        r[(2 * t) * kGRows + g] = c[u][0];
+        r[(2 * t + 1) * kGRows + g] = c[u][1];
+        r[(2 * t) * kGRows + g + 8] = c[u][2];
+        r[(2 * t + 1) * kGRows + g + 8] = c[u][3];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < kGRows * 8; idx += W * 32) {
+    for (int idx = threadIdx.x; idx < kGRows * 8 * NT; idx += W * 32) {
         const int tok = idx / kGRows;  // idx = token * 16 + row
         const int n = n0 + (idx % kGRows);
         if (tok < M && n < N) {
@@ -175,13 +187,13 @@ __global__ void __launch_bounds__(W * 32, 2)
 
 } // namespace
 
-// M <= 8, 16-bit activations, K % 64 == 0, power-of-two blocksize >= 32, 16-byte aligned A and B.
+// M <= 16, 16-bit activations, K % 64 == 0, power-of-two blocksize >= 32, 16-byte aligned A and B.
 template <typename T>
 bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                       const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,
                       int ldc, int blocksize, int quant_type, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return true;
-    if (M > 8 || K < 64 || (K % 64) != 0) return false;
+    if (M > 16 || K < 64 || (K % 64) != 0) return false;
     if (blocksize < 32 || (blocksize & (blocksize - 1)) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(B) & 15) != 0) return false;
     if (quant_type != kNF4 && quant_type != kFP4) return false;
@@ -196,8 +208,14 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
     int warps = ((long long)grid.x * 4 >= 12LL * device_sm_count()) ? 4 : 8;
     if (forced_w == 4 || forced_w == 8) warps = forced_w;
 #define BNB200_GEMV_MMA(QT, WV)                                                                                        \
-    gemv4_mma_kernel<T, QT, WV><<<grid, WV * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset,   \
-                                                              out, bias, M, N, K, ldc, l2)
+    do {                                                                                                               \
+        if (M <= 8)                                                                                                    \
+            gemv4_mma_kernel<T, QT, WV, 1><<<grid, WV * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code,      \
+                                                                         absmax_offset, out, bias, M, N, K, ldc, l2); \
+        else                                                                                                           \
+            gemv4_mma_kernel<T, QT, WV, 2><<<grid, WV * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code,      \
+                                                                         absmax_offset, out, bias, M, N, K, ldc, l2); \
+    } while (0)
     if (quant_type == kNF4) {
         if (warps == 4) BNB200_GEMV_MMA(kNF4, 4);
         else BNB200_GEMV_MMA(kNF4, 8);

@@ -139,7 +139,9 @@ class Params4bit(torch.nn.Parameter):
 
     def to(self, *args, **kwargs):
         device, dtype, non_blocking, _ = torch._C._nn._parse_to(*args, **kwargs)
-        if device is not None and device.type != "meta" and not self.bnb_quantized:
+        # quantisation happens on the first move to a CUDA device: this package has no CPU kernels, so a move of
+        # not-yet-quantised weights to the CPU (or a dtype-only .to()) keeps them as they are
+        if device is not None and device.type == "cuda" and not self.bnb_quantized:
             return self._quantize(device)
         if self.quant_state is not None:
             self.quant_state.to(device)
@@ -277,8 +279,8 @@ class Int8Params(torch.nn.Parameter):
     def to(self, *args, **kwargs):
         device, dtype, non_blocking, _ = torch._C._nn._parse_to(*args, **kwargs)
         quantized = self.data.dtype == torch.int8
-        if not quantized and device is not None and device.type != "meta" and self.data.device.type == "cpu":
-            return self._quantize(device)
+        if not quantized and device is not None and device.type == "cuda" and self.data.device.type == "cpu":
+            return self._quantize(device)  # (no CPU kernels: a move to the CPU leaves fp weights unquantised)
         new = Int8Params(super().to(device=device, dtype=dtype, non_blocking=non_blocking),
                          requires_grad=self.requires_grad, has_fp16_weights=self.has_fp16_weights)
         if quantized:

@@ -10,11 +10,11 @@ from tools.probe_perf import run_nosync, timeit
 quick = len(sys.argv) > 1 and sys.argv[1] in ("once", "once3")
 only3 = len(sys.argv) > 1 and sys.argv[1] == "once3"
 for (N, K) in ((4096, 4096), (14336, 4096), (4096, 14336)):
-    for M in (1, 2, 4, 8):
+    for M in (1, 2, 4, 8, 12, 16):
         p = make_problem(M, N, K, "nf4", "bf16")
         res = []
         for path in (0, 3, 1):
-            if (path == 0 and M > 8) or (only3 and path != 3):
+            if (path == 0 and M > 4) or (only3 and path != 3):
                 continue
             nat.lib.cbnb_b200_gemm_4bit_force_path(path)
             if quick:

@@ -92,9 +92,9 @@ def time_shapes(shapes):
         parts = []
         t, m = timeit(lambda: run_old_nosync(p, out), iters=15)
         parts.append(f"one-CTA {t:.1f} us ({fl/t/1e6:.0f} TF)")
-        for xl in ("0", "1"):
+        for xl in ("0",):
             os.environ["BNB_B200_PAIR_XLOCAL"] = xl
-            for mt, sp in ((256, 1), (384, 0), (384, 1)):
+            for mt, sp in ((256, 0), (256, 1), (384, 0), (384, 1)):
                 t, m = timeit(lambda: run_pair(p, mt, sp, out=out, sync=False), iters=15)
                 parts.append(f"pair xl={xl} mt={mt} sp={sp} {t:.1f} us ({fl/t/1e6:.0f} TF, min {m:.1f})")
         os.environ["BNB_B200_PAIR_XLOCAL"] = "0"
@@ -126,15 +126,16 @@ def trace(shape, mt):
             print(f"{i:3d} " + " ".join(f"{(t[cta][r][i] - base) if t[cta][r][i] else -1:11d}" for r in range(8)))
         print(f"  epilogue begin {t[cta][8][0]-base}, end {t[cta][9][0]-base}")
         if cta == 0:
-            wx = (t[0][1][4:nst] - t[0][2][3:nst - 1]).astype(np.int64)   # wait for the activation bytes after the previous issue
-            wa = (t[0][7][4:nst] - t[0][1][4:nst]).astype(np.int64)       # additional wait for the decoded weights
-            xl = (t[0][1][4:nst] - t[0][0][4:nst]).astype(np.int64)       # activation load: issue -> seen by the MMA thread
-            print(f"  MMA thread: waits x_full {np.median(wx):.0f} (p90 {np.percentile(wx,90):.0f}), then a_full {np.median(wa):.0f} "
-                  f"(p90 {np.percentile(wa,90):.0f}); x issue->seen {np.median(xl):.0f} (p90 {np.percentile(xl,90):.0f})")
-        if cta == 0:
-            full = t[0][1][:nst].astype(np.int64)
-            d = np.diff(full)
-            print(f"  MMA stage period: mean {d[4:].mean():.0f}  median {np.median(d[4:]):.0f}  p90 {np.percentile(d[4:], 90):.0f}  max {d[4:].max()}")
+            iss = (t[0][2][4:nst] - t[0][1][4:nst]).astype(np.int64)      # MMAs + probes + commits of a stage
+            tail = (t[0][7][4:nst] - t[0][2][4:nst]).astype(np.int64)     # fallback waits after a failed probe
+            xl = (t[0][1][4:nst] - t[0][0][4:nst]).astype(np.int64)       # activation load: issue -> stage start
+            print(f"  MMA thread: issue block {np.median(iss):.0f} (p90 {np.percentile(iss,90):.0f}), fallback waits {np.median(tail):.0f} "
+                  f"(p90 {np.percentile(tail,90):.0f}); x issue->stage start {np.median(xl):.0f} (p90 {np.percentile(xl,90):.0f})")
+            for st in (0, 1):
+                mt_ = t[0][9][1 + 16 * st: 1 + 16 * st + 12].astype(np.int64)
+                mt_ = mt_[mt_ > 0]
+                if len(mt_) > 1:
+                    print(f"  a-stage {24 + st} issue deltas (after each tcgen05.mma, then the two commits): " + " ".join(str(int(v)) for v in np.diff(mt_)))
         dm = (t[cta][4][:nst] - t[cta][3][:nst]).astype(np.int64)
         de = (t[cta][5][:nst] - t[cta][4][:nst]).astype(np.int64)
         da = (t[cta][6][:nst] - t[cta][5][:nst]).astype(np.int64)
@@ -151,7 +152,7 @@ if __name__ == "__main__":
         time_shapes(shapes or [(4096, 4096, 4096), (4096, 11008, 4096), (4096, 4096, 11008), (2048, 14336, 4096),
                                (1024, 4096, 4096), (512, 4096, 4096), (8192, 8192, 8192)])
     if not args or "trace" in args:
-        for xl in ("0", "1"):
+        for xl in ("0",):
             os.environ["BNB_B200_PAIR_XLOCAL"] = xl
             print(f"===== BNB_B200_PAIR_XLOCAL={xl}")
             for mt in (256, 384):

@@ -37,6 +37,17 @@ _8BIT_BLOCKSIZES = (64, 128, 256, 512, 1024, 2048, 4096)
 _raw_stream = torch._C._cuda_getCurrentRawStream
 
 
+_INT32_MAX = 2**31 - 1
+
+
+def _check_sizes(what: str, *sizes: int) -> None:
+    """The C ABI carries element counts and dimensions as 32-bit ints (as the reference's does, reference
+    csrc/pythonInterface.cpp:343-616): refuse anything that would wrap instead of processing a prefix silently."""
+    for v in sizes:
+        if v > _INT32_MAX:
+            raise ValueError(f"{what}: size {v} exceeds the 32-bit range of the native interface")
+
+
 def _stream(t: torch.Tensor) -> int:
     return _raw_stream(t.device.index)
 
@@ -80,6 +91,7 @@ def _quantize_blockwise(A: torch.Tensor, code: torch.Tensor, blocksize: int):
     sfx = _suffix(A.dtype, "Blockwise quantization")
     A = A.contiguous()
     n = A.numel()
+    _check_sizes("quantize_blockwise", n)
     absmax = torch.empty((-(n // -blocksize),), device=A.device, dtype=torch.float32)
     out = torch.empty_like(A, dtype=torch.uint8)
     with _on_device(A):
@@ -92,6 +104,7 @@ def _quantize_blockwise(A: torch.Tensor, code: torch.Tensor, blocksize: int):
 def _dequantize_blockwise_into(A, absmax, code, blocksize, dtype, out) -> None:
     sfx = _suffix(dtype, "Blockwise dequantization")
     A = A.contiguous()
+    _check_sizes("dequantize_blockwise", A.numel())
     with _on_device(A):
         getattr(lib, f"cdequantize_blockwise_{sfx}")(code.data_ptr(), A.data_ptr(), absmax.data_ptr(), out.data_ptr(),
                                                      blocksize, A.numel(), _stream(A))
@@ -123,6 +136,7 @@ def _quantize_4bit(A: torch.Tensor, blocksize: int, quant_type: str, quant_stora
     sfx = _suffix(A.dtype, "Blockwise 4bit quantization")
     A = A.contiguous()
     n = A.numel()
+    _check_sizes("quantize_4bit", n)
     absmax = torch.empty((-(n // -blocksize),), device=A.device, dtype=torch.float32)
     out = torch.empty(((n + 1) // (quant_storage.itemsize * 2), 1), device=A.device, dtype=quant_storage)
     with _on_device(A):
@@ -137,6 +151,7 @@ def _dequantize_4bit_into(A, absmax, blocksize, quant_type, dtype, out) -> None:
         raise ValueError(f"quant_type must be nf4 or fp4, got {quant_type}")
     sfx = _suffix(dtype, "Blockwise 4bit dequantization")
     A = A.contiguous()
+    _check_sizes("dequantize_4bit", out.numel())
     with _on_device(A):
         getattr(lib, f"cdequantize_blockwise_{sfx}_{quant_type}")(None, A.data_ptr(), absmax.data_ptr(),
                                                                   out.data_ptr(), blocksize, out.numel(), _stream(A))
@@ -169,6 +184,7 @@ def gemm_4bit_into(A, B, shapeB, absmax, blocksize, quant_type, bias, absmax_8bi
     N = shapeB[0]
     if K != shapeB[1]:
         raise RuntimeError(f"A inner dim ({K}) does not match weight ({shapeB[1]})")
+    _check_sizes("gemm_4bit", M, N, K, ldc)
     if absmax.dtype != torch.float32:
         raise RuntimeError(f"absmax must be float32, got {absmax.dtype}")
     if quant_type not in _QT_ID:
@@ -300,9 +316,19 @@ def _int8_matmul_into(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor):
                              _stream(A))
     lib.check("int8_linear_matmul")
     if rc == 100:
-        # inner dimension not a multiple of 16 bytes (TMA row pitch): the reference's own
-        # escape hatch for K % 4 != 0 (reference backends/cuda/ops.py:126-128), still on the GPU.
-        return out.copy_(torch.matmul(A.float(), B.float().t()).to(torch.int32))
+        # inner dimension not a multiple of 16 bytes (TMA row pitch) or unaligned views: zero-pad K to the next
+        # multiple of 16 (zeros add nothing to an integer dot product) and run the same exact kernel.  (The
+        # reference's escape hatch for K % 4 != 0 is an fp32 matmul, reference backends/cuda/ops.py:126-128, which
+        # is only exact below 2^24.)
+        Kp = -(-K // 16) * 16
+        Ap = torch.zeros((M, Kp), device=A.device, dtype=torch.int8)
+        Bp = torch.zeros((N, Kp), device=A.device, dtype=torch.int8)
+        Ap[:, :K] = A.reshape(M, K)
+        Bp[:, :K] = B
+        with _on_device(A):
+            rc = lib.cigemmlt_32(lib.get_context(), N, M, Kp, Bp.data_ptr(), Ap.data_ptr(), out.data_ptr(), None, Kp, Kp,
+                                 N, _stream(A))
+        lib.check("int8_linear_matmul (padded K)")
     if rc != 0:
         raise RuntimeError(f"int8 GEMM failed (code {rc}): A={tuple(A.shape)} B={tuple(B.shape)}")
     return out

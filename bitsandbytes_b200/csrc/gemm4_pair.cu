@@ -125,9 +125,7 @@ template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams&
     }
 }
 
-// XLOCAL: every CTA's activation bytes complete on its OWN barrier and the peer forwards one (relaxed) arrive per
-// stage to the leader, instead of the cta_group::2 TMA form whose complete_tx crosses to the leader's barrier.
-template <typename T, int QT, int MT, bool TRACE, bool XLOCAL>
+template <typename T, int QT, int MT, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ OutMaps omaps, const PairParams p) {
@@ -142,12 +140,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint8_t* sx = smem;                                   // [kNX][kNSub][kBoxRows x 128 B]
     uint8_t* sw = smem + kNX * kXStageBytes;              // [kNC][128 x 64 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sw + kNC * kCodeStageBytes);
-    uint64_t* full = bars;                  // [kNA]  decode warps of both CTAs -> MMA   (leader's is used)
-    uint64_t* empty = bars + kNA;           // [kNA]  MMA -> decode warps (A slot free)
-    uint64_t* x_full = empty + kNA;         // [kNX]  activation bytes -> MMA            (leader's is used)
-    uint64_t* x_empty = x_full + kNX;       // [kNX]  MMA -> activation producer
-    uint64_t* x_local = x_empty + kNX;      // [kNX]  XLOCAL, peer: own bytes landed -> forwarder
-    uint64_t* c_full = x_local + kNX;       // [kNC]
+    // ONE barrier pair per a-stage, indexed by the activation slot i % kNX (the TMEM A slot is i % kNA):
+    //   full[i % kNX]   the stage's activation bytes (both CTAs) + the 8 decode warps (both CTAs) -> MMA  (leader's)
+    //   empty[i % kNX]  MMA(i) has retired -> the activation producer (slot reusable at stage i + kNX) AND the
+    //                   decode warps (TMEM A slot reusable at stage i + kNA <= i + kNX)
+    // so the MMA thread pays one wait and one commit per stage while the activation ring is deeper than the A ring.
+    uint64_t* full = bars;                  // [kNX]
+    uint64_t* empty = bars + kNX;           // [kNX]
+    uint64_t* c_full = empty + kNX;         // [kNC]
     uint64_t* c_empty = c_full + kNC;       // [kNC]
     uint64_t* acc_full = c_empty + kNC;     // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -182,16 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
-        for (int s = 0; s < kNA; ++s) {
-            ptx::mbar_init(&full[s], 8);  // the 4 decode warps of each CTA (leader's barrier; the peer's is unused)
-            ptx::mbar_init(&empty[s], 1);
-        }
         for (int s = 0; s < kNX; ++s) {
-            // cta_group::2 loads: the leader's producer arms the bytes of both CTAs (1 arrival);
-            // XLOCAL: its own bytes (1 arrival) + the peer's forwarded "my bytes have landed" (1 arrival)
-            ptx::mbar_init(&x_full[s], XLOCAL ? 2 : 1);
-            ptx::mbar_init(&x_empty[s], 1);
-            ptx::mbar_init(&x_local[s], 1);
+            // leader: its producer's expect_tx arrival (bytes of both CTAs) + the 4 decode warps of each CTA
+            ptx::mbar_init(&full[s], 9);
+            ptx::mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < kNC; ++s) {
             ptx::mbar_init(&c_full[s], 1);
@@ -212,28 +206,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 0) {
         // ================================================================== activation producer
         if (lane == 0) {
-            const uint32_t lead_xfull0 = ptx::mapa_u32(ptx::smem_u32(&x_full[0]), 0);
+            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&x_empty[s], ph ^ 1u, 1, i);
+                ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, i);  // MMA(i - kNX) has retired
                 trace_ev<TRACE>(p, 0, i);
                 const int k0 = (st_begin + i) * kAK;
+                if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * kXStageBytes);
                 uint8_t* dst = sx + s * kXStageBytes;
-                if constexpr (XLOCAL) {
-                    uint64_t* bar = leader ? &x_full[s] : &x_local[s];
-                    ptx::mbar_arrive_expect_tx(bar, kXStageBytes);
 #pragma unroll
-                    for (int sub = 0; sub < Cfg::kNSub; ++sub)
-                        ptx::tma_load_2d(dst + sub * Cfg::kSubBytes, &tmap_x, bar, k0,
-                                         m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
-                } else {
-                    if (leader) ptx::mbar_arrive_expect_tx(&x_full[s], 2 * kXStageBytes);
-#pragma unroll
-                    for (int sub = 0; sub < Cfg::kNSub; ++sub)
-                        ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_xfull0 + 8u * s, k0,
-                                              m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
-                }
+                for (int sub = 0; sub < Cfg::kNSub; ++sub)
+                    ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_full0 + 8u * s, k0,
+                                          m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
                 if (++s == kNX) {
                     s = 0;
                     ph ^= 1u;
@@ -258,92 +243,68 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (!leader) {
-            if constexpr (XLOCAL) {
-                // ========================================================== forwarder (peer CTA)
-                // "my half of activation stage xs is in my shared memory": one relaxed cluster-scope arrive on
-                // the leader's barrier (the payload was written by the async proxy and is read by the tensor core
-                // after the MMA thread's own acquire of that barrier: nothing for a release fence to publish)
-                const uint32_t lead_xfull0 = ptx::mapa_u32(ptx::smem_u32(&x_full[0]), 0);
-                int xs = 0;
-                uint32_t xph = 0;
-                for (int i = 0; i < nst; ++i) {
-                    ptx::mbar_wait_bounded(&x_local[xs], xph, 3, i);
-                    if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_xfull0 + 8u * xs);
-                    __syncwarp();
-                    if (++xs == kNX) {
-                        xs = 0;
-                        xph ^= 1u;
-                    }
+        // ================================================================== MMA issuer (leader CTA, one thread)
+        // Measured on B200 (round 2 traces, profiles/r02_pair_trace.md): the tensor core accepts a tcgen05.mma only
+        // about one instruction ahead of the one it executes (an N = 192 pair MMA is accepted every ~95 cycles), a
+        // multicast tcgen05.commit costs this thread ~100 cycles and an mbarrier probe ~70.  Anything done BETWEEN two
+        // stages therefore drains the pipe.  So the loop is software-pipelined: the commit that releases stage i-1 is
+        // issued after the second MMA of stage i (it then also covers those two: the slots are released ~200 cycles
+        // later, which the rings absorb), and the barrier of stage i+1 is probed (one non-blocking try_wait) before
+        // the last MMAs of stage i -- the operands are ready long before, the probe succeeds and its latency hides
+        // under the queued MMAs; only a failed probe falls back to a blocking wait.
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc =
+                ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
+            constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
+            int s = 0, xs = 0, pxs = 0;
+            uint32_t xph = 0;
+            ptx::mbar_wait_bounded(&full[0], 0, 4, 0);
+            for (int i = 0; i < nst; ++i) {
+                trace_ev<TRACE>(p, 1, i);
+                ptx::tc_fence_after();
+                int nxs = xs + 1;
+                uint32_t nxph = xph;
+                if (nxs == kNX) {
+                    nxs = 0;
+                    nxph ^= 1u;
                 }
-            }
-        } else {
-            // ============================================================== MMA issuer (leader CTA)
-            // One thread runs the whole loop.  Measured on B200 (round 2 traces): the tensor core accepts a
-            // tcgen05.mma only about one instruction ahead of the one it executes, so every cycle this thread spends
-            // in an mbarrier wait or a commit BETWEEN stages drains the pipe (two waits + two commits cost ~550 of
-            // 1300 cycles per stage).  The waits for stage i+1 are therefore issued as single non-blocking probes IN
-            // THE MIDDLE of stage i's MMAs -- the operands are ready long before, the probes succeed, and their
-            // latency hides under the MMAs still queued; only a failed probe falls back to a blocking wait.
-            if (lane == 0) {
-                constexpr uint32_t idesc =
-                    ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
-                constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
-                int s = 0, xs = 0;
-                uint32_t ph = 0, xph = 0;
-                ptx::mbar_wait_bounded(&x_full[0], 0, 4, 0);
-                ptx::mbar_wait_bounded(&full[0], 0, 8, 0);
-                for (int i = 0; i < nst; ++i) {
-                    trace_ev<TRACE>(p, 1, i);
-                    ptx::tc_fence_after();
-                    int ns = s + 1, nxs = xs + 1;
-                    uint32_t nph = ph, nxph = xph;
-                    if (ns == kNA) {
-                        ns = 0;
-                        nph ^= 1u;
-                    }
-                    if (nxs == kNX) {
-                        nxs = 0;
-                        nxph ^= 1u;
-                    }
-                    const bool more = i + 1 < nst;
-                    bool okx = false, oka = false;
-                    const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
-                    const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
-                    // TRACE builds: per-instruction issue times of a-stages 24 and 25 (role 9, entries 1..)
-                    const bool micro = TRACE && (i == 24 || i == 25);
-                    int mslot = 1 + (i - 24) * 16;
-                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
+                const bool more = i + 1 < nst;
+                bool ok = false;
+                const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
+                const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
+                // TRACE builds: per-instruction issue times of a-stages 24 and 25 (role 9, entries 1..)
+                const bool micro = TRACE && (i == 24 || i == 25);
+                int mslot = 1 + (i - 24) * 16;
+                if (micro) trace_ev<TRACE>(p, 9, mslot++);
 #pragma unroll
-                    for (int j = 0; j < kMmas; ++j) {
-                        const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
-                        // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
-                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
-                        ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
-                                             (i | k) != 0 ? 1u : 0u);
+                for (int j = 0; j < kMmas; ++j) {
+                    const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
+                    // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
+                    const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
+                    ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
+                                         (i | k) != 0 ? 1u : 0u);
+                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
+                    if (j == 1 && i > 0) {
+                        ptx::tc_commit_pair(&empty[pxs], 0x3);  // stage i-1 (and the two MMAs above) retired -> slots free
                         if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                        if (j == kMmas / 2 - 1 && more) okx = ptx::mbar_try_wait(&x_full[nxs], nxph);
-                        if (j == kMmas - 2 && more) oka = ptx::mbar_try_wait(&full[ns], nph);
                     }
-                    ptx::tc_commit_pair(&empty[s], 0x3);
-                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                    ptx::tc_commit_pair(&x_empty[xs], 0x3);
-                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                    if (i == nst - 1) ptx::tc_commit_pair(acc_full, 0x3);
-                    trace_ev<TRACE>(p, 2, i);
-                    if (more) {
-                        if (!okx) ptx::mbar_wait_bounded(&x_full[nxs], nxph, 4, i + 1);
-                        if (!oka) ptx::mbar_wait_bounded(&full[ns], nph, 8, i + 1);
+                    if (j == kMmas - 2 && more) {
+                        ok = ptx::mbar_try_wait(&full[nxs], nxph);
+                        if (micro) trace_ev<TRACE>(p, 9, mslot++);
                     }
-                    trace_ev<TRACE>(p, 7, i);
-                    s = ns;
-                    ph = nph;
-                    xs = nxs;
-                    xph = nxph;
                 }
+                trace_ev<TRACE>(p, 2, i);
+                if (more && !ok) ptx::mbar_wait_bounded(&full[nxs], nxph, 4, i + 1);
+                trace_ev<TRACE>(p, 7, i);
+                pxs = xs;
+                xs = nxs;
+                xph = nxph;
+                if (++s == kNA) s = 0;
             }
-            __syncwarp();
+            ptx::tc_commit_pair(&empty[pxs], 0x3);
+            ptx::tc_commit_pair(acc_full, 0x3);
         }
+        __syncwarp();
     } else {
         // ================================================================== decode warps
         const int dw = warp - 2;        // 0..15
@@ -380,8 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int t = t0 + j;
                 if (t < cnt) {
                     const int i = 4 * t + grp;
-                    const int s = i % kNA;
-                    const uint32_t ph = (uint32_t)(i / kNA) & 1u;
+                    const int s = i % kNA;   // TMEM A slot
+                    const int xs = i % kNX;  // barrier (activation) slot of this stage
                     const int cj = i >> 1;
                     const int cs = cj % kNC;
                     const uint32_t cph = (uint32_t)(cj / kNC) & 1u;
@@ -412,7 +373,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);
                     if (tracer) trace_ev<TRACE>(p, 4, i);
 
-                    ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 6, i);
+                    // TMEM A slot s was last read by MMA(i - kNA), which commits to empty[(i - kNA) % kNX]
+                    if (i >= kNA) {
+                        const int q = i - kNA;
+                        ptx::mbar_wait_bounded(&empty[q % kNX], (uint32_t)(q / kNX) & 1u, 6, i);
+                    }
                     if (tracer) trace_ev<TRACE>(p, 5, i);
                     ptx::tc_fence_after();
                     ptx::tmem_st_x32(tmem_base + (uint32_t(quarter * 32) << 16) + kACol0 + s * 32, r);
@@ -423,9 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                         // "this warp's 32 rows of A slot s are in TMEM": the payload is tensor memory, completed by
                         // wait::st above -- no generic-proxy data to release, hence the relaxed remote arrive
                         if (leader)
-                            ptx::mbar_arrive(&full[s]);
+                            ptx::mbar_arrive(&full[xs]);
                         else
-                            ptx::mbar_arrive_cluster_relaxed(lead_full0 + 8u * s);
+                            ptx::mbar_arrive_cluster_relaxed(lead_full0 + 8u * xs);
                     }
                     if (tracer) trace_ev<TRACE>(p, 6, i);
                 }
@@ -575,10 +540,10 @@ bool cached_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle
     return true;
 }
 
-template <typename T, int QT, int MT, bool TRACE, bool XLOCAL>
+template <typename T, int QT, int MT, bool TRACE>
 bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_splits) {
     using Cfg = PairCfg<MT>;
-    auto kern = gemm4_pair_kernel<T, QT, MT, TRACE, XLOCAL>;
+    auto kern = gemm4_pair_kernel<T, QT, MT, TRACE>;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};  // the opt-in is per device
@@ -750,21 +715,11 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
     p.log2_bs = ilog2_pow2(blocksize);
     p.ka_total = K / kAK;
 
-    // A/B switch (read per call so that one process can compare): BNB_B200_PAIR_XLOCAL=1 -> per-CTA activation
-    // barriers + forwarded arrive instead of cta_group::2 TMA loads completing on the leader's barrier
-    const char* xl = getenv("BNB_B200_PAIR_XLOCAL");
-    const bool xlocal = xl != nullptr && xl[0] == '1';
 #define BNB200_PAIR_MT(QT, TR)                                                                                         \
     switch (MT) {                                                                                                      \
-    case 128:                                                                                                          \
-        return xlocal ? launch_pair_mt<T, QT, 128, TR, true>(A, p, stream, force_splits)                               \
-                      : launch_pair_mt<T, QT, 128, TR, false>(A, p, stream, force_splits);                             \
-    case 256:                                                                                                          \
-        return xlocal ? launch_pair_mt<T, QT, 256, TR, true>(A, p, stream, force_splits)                               \
-                      : launch_pair_mt<T, QT, 256, TR, false>(A, p, stream, force_splits);                             \
-    default:                                                                                                           \
-        return xlocal ? launch_pair_mt<T, QT, 384, TR, true>(A, p, stream, force_splits)                               \
-                      : launch_pair_mt<T, QT, 384, TR, false>(A, p, stream, force_splits);                             \
+    case 128: return launch_pair_mt<T, QT, 128, TR>(A, p, stream, force_splits);                                       \
+    case 256: return launch_pair_mt<T, QT, 256, TR>(A, p, stream, force_splits);                                       \
+    default: return launch_pair_mt<T, QT, 384, TR>(A, p, stream, force_splits);                                        \
     }
     if (trace != nullptr) {
         if (quant_type == kNF4) {

@@ -81,15 +81,13 @@ def test_reference_python_layer_runs_on_our_library(tmp_path):
     q, qs = F.quantize_4bit(W, quant_type="nf4")
     assert same(q, ref["q"]) and same(qs.absmax, ref["absmax"]) and same(F.dequantize_4bit(q, qs), ref["deq"])
     for M in (1, 8, 700):
+        # The reference's Python layer picks its own route per shape (its legacy gemv symbol for one token, its
+        # dequantize + cuBLAS fallback on sm_100 for most others, reference backends/cuda/ops.py:583-623, 904-916),
+        # so its result and our fused GEMM's share the weights but not the fp32 summation order: the tolerance is
+        # BASELINE.json's (<= 1e-3 relative for bf16 GEMM outputs); everything elementwise below is bit for bit.
         ours = bnb.matmul_4bit(ref[f"x{M}"].cuda(), q.t(), qs)
-        if M == 1:
-            # the reference's Python layer may route a single token to its legacy gemv symbol
-            # (cgemm_4bit_inference_naive_*), which this library serves with the generic CUDA-core kernel: same
-            # weights and products, another fp32 summation order than the GEMV our own layer dispatches
-            rel = (ours.float().cpu() - ref["y1"].float()).norm() / ref["y1"].float().norm()
-            assert rel.item() < 5e-3, rel.item()
-        else:
-            assert same(ours, ref[f"y{M}"]), f"matmul_4bit M={M}"
+        rel = (ours.float().cpu() - ref[f"y{M}"].float()).norm() / ref[f"y{M}"].float().norm()
+        assert rel.item() <= 1e-3, (M, rel.item())
     q8, st = F.quantize_blockwise(ref["A8"].cuda(), blocksize=256)
     assert same(q8, ref["q8"]) and same(st.absmax, ref["absmax8"]) and same(F.dequantize_blockwise(q8, st), ref["deq8"])
     CA, SCA, cols = F.int8_vectorwise_quant(ref["Ah"].cuda(), threshold=6.0)

@@ -286,8 +286,19 @@ __device__ __forceinline__ void build_q8_bracket(const float* __restrict__ scode
         sbr[t] = q8_count_below(scode, q8_cell_low(t)) | (q8_count_below(scode, q8_cell_low(t + 1)) << 16);
 }
 
+// final decision table, entry c: { midpoint of the two candidate entries, candidate p | other o << 8 | (p < c) << 16 }
+// (the reference's midpoint rule with the midpoint precomputed once per CTA instead of two code look-ups per element)
+__device__ __forceinline__ void build_q8_final(const float* __restrict__ scode, float2* __restrict__ sfin) {
+    for (int c = threadIdx.x; c <= 256; c += blockDim.x) {
+        const uint32_t po = q8_structure(c);
+        const unsigned p = (po & 0xffffu) >> 2, o = (po >> 16) >> 2;
+        const float midpoint = mul_ftz(scode[o] + scode[p], 0.5f);
+        sfin[c] = make_float2(midpoint, __uint_as_float(p | (o << 8) | ((p < (unsigned)c ? 1u : 0u) << 16)));
+    }
+}
+
 __device__ __forceinline__ unsigned quantize_8bit_fast(const float* __restrict__ scode,
-                                                       const uint32_t* __restrict__ spo,
+                                                       const float2* __restrict__ sfin,
                                                        const uint32_t* __restrict__ sbr, float x) {
     // value cell: magnitude key, everything tiny (and NaN, whose key is out of range) -> 0; zero counts as positive
     unsigned cm = ((__float_as_uint(x) & 0x7fffffffu) >> 19) - (unsigned)kQ8MinKey;
@@ -298,17 +309,15 @@ __device__ __forceinline__ unsigned quantize_8bit_fast(const float* __restrict__
     const unsigned hi = br >> 16;
     while (c < hi && scode[c] < x) ++c;
     c = (x == x) ? c : 0u;  // NaN (0 * rcp(0)): no entry is below it
-    const uint32_t po = spo[c];
-    const char* cb = reinterpret_cast<const char*>(scode);
-    const unsigned p4 = po & 0xffffu, o4 = po >> 16;
-    const float midpoint = mul_ftz(*reinterpret_cast<const float*>(cb + o4) + *reinterpret_cast<const float*>(cb + p4), 0.5f);
-    const bool move = (p4 < 4u * c) ? (x > midpoint) : (x < midpoint);
-    return (move ? o4 : p4) >> 2;
+    const float2 f = sfin[c];
+    const unsigned w = __float_as_uint(f.y);
+    const bool move = (w >> 16) ? (x > f.x) : (x < f.x);
+    return move ? ((w >> 8) & 0xffu) : (w & 0xffu);
 }
 
 template <int QT>
-__device__ __forceinline__ unsigned quantize_8bit_any(const float* scode, const uint32_t* spo, const uint32_t* sbr, float x) {
-    return QT == kGeneral8bitFast ? quantize_8bit_fast(scode, spo, sbr, x) : quantize_8bit(scode, x);
+__device__ __forceinline__ unsigned quantize_8bit_any(const float* scode, const float2* sfin, const uint32_t* sbr, float x) {
+    return QT == kGeneral8bitFast ? quantize_8bit_fast(scode, sfin, sbr, x) : quantize_8bit(scode, x);
 }
 
 constexpr int kQThreads = 256;
@@ -323,26 +332,15 @@ __global__ void __launch_bounds__(kQThreads)
     constexpr int V = kQEPT / VE; // vectors per thread
     __shared__ float scode[256];
     __shared__ float swarp[kQThreads / 32];
-    __shared__ uint32_t spo[QT == kGeneral8bitFast ? 257 : 1];
+    __shared__ float2 sfin[QT == kGeneral8bitFast ? 257 : 1];
     __shared__ uint32_t sbr[QT == kGeneral8bitFast ? kQ8Cells : 1];
     __shared__ float2 q4lut[QT == kNF4 ? kQ4LutNF4 : (QT == kFP4 ? kQ4LutFP4 : 1)];
     constexpr bool k8 = QT == kGeneral8bit || QT == kGeneral8bitFast;
-
-    if (k8) {
-        scode[threadIdx.x] = code[threadIdx.x];
-        if (QT == kGeneral8bitFast) {
-            spo[threadIdx.x] = q8_structure(threadIdx.x);
-            if (threadIdx.x == 0) spo[256] = q8_structure(256);
-        }
-        __syncthreads();
-        if (QT == kGeneral8bitFast) {
-            build_q8_bracket(scode, sbr);
-            __syncthreads();
-        }
-    } else {
-        if (threadIdx.x < (QT == kNF4 ? kQ4LutNF4 : kQ4LutFP4)) build_q4_lut<QT>(q4lut, threadIdx.x);
-        __syncthreads();
-    }
+    // the code book's own (cold, 1 KB) fetch is issued first and parked in a register; the look-up tables are built
+    // AFTER the first tile's loads are in flight, so neither latency delays the data
+    float creg = 0.f;
+    if (k8) creg = __ldg(code + threadIdx.x);
+    bool tables_ready = false;
 
     const int bs = 1 << log2_bs;
     const int G = bs / kQEPT;           // threads per quant block (>= 2)
@@ -355,6 +353,21 @@ __global__ void __launch_bounds__(kQThreads)
         float x[V][VE];
 #pragma unroll
         for (int v = 0; v < V; ++v) VecIO<T>::load(A + blk_base + (long long)(j + v * G) * VE, x[v]);
+        if (!tables_ready) {
+            tables_ready = true;
+            if (k8) {
+                scode[threadIdx.x] = creg;
+                __syncthreads();
+                if (QT == kGeneral8bitFast) {
+                    build_q8_final(scode, sfin);
+                    build_q8_bracket(scode, sbr);
+                    __syncthreads();
+                }
+            } else {
+                if (threadIdx.x < (QT == kNF4 ? kQ4LutNF4 : kQ4LutFP4)) build_q4_lut<QT>(q4lut, threadIdx.x);
+                __syncthreads();
+            }
+        }
 
         float m = -3.402823466e+38f;
 #pragma unroll
@@ -387,10 +400,10 @@ __global__ void __launch_bounds__(kQThreads)
                 uint32_t w[VE / 4];
 #pragma unroll
                 for (int q = 0; q < VE / 4; ++q) {
-                    uint32_t b0 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 0], inv));
-                    uint32_t b1 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 1], inv));
-                    uint32_t b2 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 2], inv));
-                    uint32_t b3 = quantize_8bit_any<QT>(scode, spo, sbr, mul_ftz(x[v][4 * q + 3], inv));
+                    uint32_t b0 = quantize_8bit_any<QT>(scode, sfin, sbr, mul_ftz(x[v][4 * q + 0], inv));
+                    uint32_t b1 = quantize_8bit_any<QT>(scode, sfin, sbr, mul_ftz(x[v][4 * q + 1], inv));
+                    uint32_t b2 = quantize_8bit_any<QT>(scode, sfin, sbr, mul_ftz(x[v][4 * q + 2], inv));
+                    uint32_t b3 = quantize_8bit_any<QT>(scode, sfin, sbr, mul_ftz(x[v][4 * q + 3], inv));
                     w[q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
                 }
                 if (VE == 4)
@@ -467,9 +480,11 @@ template <typename T, int QT>
 void launch_quantize_blockwise(const float* code, const T* A, float* absmax, uint8_t* out, int blocksize, long long n,
                                cudaStream_t stream) {
     if (QT == kGeneral8bit) {
+        // default: the bracket-table search (bit-identical, CPU-proven and GPU-tested); BNB_B200_Q8_WALK=1 keeps the
+        // reference's 7-step walk for A/B measurements
         static const bool fast = [] {
-            const char* e = getenv("BNB_B200_Q8_FAST");
-            return e != nullptr && e[0] == '1';  // experimental, not yet run on a GPU: off
+            const char* e = getenv("BNB_B200_Q8_WALK");
+            return !(e != nullptr && e[0] == '1');
         }();
         if (fast) {
             launch_quantize_blockwise_impl<T, kGeneral8bitFast>(code, A, absmax, out, blocksize, n, stream);

@@ -86,6 +86,7 @@ struct PairParams {
     float* ws_partial;   // [split slots][MT columns][128 rows] fp32
     int* ws_counter;     // one per split (tile, CTA rank); zero on entry, reset by the last arriver
     long long* trace;    // TRACE builds only
+    int trace_lite;      // 1: only the per-tile landmarks (first MMA, last MMA issued, accumulator ready, epilogue done)
     int M, N, K, ldc;
     int log2_bs;
     int ka_total;        // a-stages in K
@@ -118,10 +119,20 @@ template <int MT> struct PairCfg {
     static_assert(kSubBytes % 1024 == 0, "128-byte swizzle atoms");
 };
 
-template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams& p, int role, int i) {
+template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams& p, int role, int i, bool landmark = false) {
     if constexpr (TRACE) {
-        if (p.trace != nullptr && blockIdx.x < 2 && i < kTraceStages)
+        if (p.trace != nullptr && blockIdx.x < 2 && i < kTraceStages && (landmark || !p.trace_lite))
             p.trace[((long long)blockIdx.x * kTraceRoles + role) * kTraceStages + i] = clock64();
+    }
+}
+// wall clock (ns) next to a cycle stamp, to convert cycles into time
+template <bool TRACE> __device__ __forceinline__ void trace_ns(const PairParams& p, int role, int i) {
+    if constexpr (TRACE) {
+        if (p.trace != nullptr && blockIdx.x < 2) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[((long long)blockIdx.x * kTraceRoles + role) * kTraceStages + i] = (long long)t;
+        }
     }
 }
 
@@ -260,7 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint32_t xph = 0;
             ptx::mbar_wait_bounded(&full[0], 0, 4, 0);
             for (int i = 0; i < nst; ++i) {
-                trace_ev<TRACE>(p, 1, i);
+                trace_ev<TRACE>(p, 1, i, i == 0);
+                if (i == 0) trace_ns<TRACE>(p, 9, 40);
                 ptx::tc_fence_after();
                 int nxs = xs + 1;
                 uint32_t nxph = xph;
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         if (micro) trace_ev<TRACE>(p, 9, mslot++);
                     }
                 }
-                trace_ev<TRACE>(p, 2, i);
+                trace_ev<TRACE>(p, 2, i, i == nst - 1);
                 if (more && !ok) ptx::mbar_wait_bounded(&full[nxs], nxph, 4, i + 1);
                 trace_ev<TRACE>(p, 7, i);
                 pxs = xs;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ================================================================== epilogue
         ptx::mbar_wait_bounded(acc_full, 0, 7);
         ptx::tc_fence_after();
-        if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0);
+        if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0, true);
 
         // this warp: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4) (= tokens)
         constexpr int kColsPerWarp = MT / 4;  // 32, 64 or 96
@@ -488,7 +500,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
         }
-        if (tracer && grp == 0) trace_ev<TRACE>(p, 9, 0);
+        if (tracer && grp == 0) {
+            trace_ev<TRACE>(p, 9, 0, true);
+            trace_ns<TRACE>(p, 9, 41);
+        }
     }
 
     // ------------------------------------------------------------------ teardown
@@ -708,6 +723,10 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
     p.n_peers = n_peers;
     for (int r = 0; r < n_peers; ++r) p.peer_out[r] = peers[r];
     p.trace = trace;
+    {
+        const char* tl = getenv("BNB_B200_TRACE_LITE");
+        p.trace_lite = (tl != nullptr && tl[0] == '1') ? 1 : 0;
+    }
     p.M = M;
     p.N = N;
     p.K = K;

@@ -77,6 +77,20 @@ static float cell_low(int t) {
 static void build_bracket(const float* code, uint32_t* br) {
     for (int t = 0; t < Q8_CELLS; ++t) br[t] = count_below(code, cell_low(t)) | (count_below(code, cell_low(t + 1)) << 16);
 }
+/* build_q8_final: entry c = { midpoint of the two candidates, p | o << 8 | (p < c) << 16 } */
+typedef struct { float mid; uint32_t w; } fin_t;
+static void build_final(const float* code, fin_t* fin) {
+    for (int c = 0; c <= 256; ++c) {
+        const uint32_t po = g_po[c];
+        const unsigned p = (po & 0xffffu) >> 2, o = (po >> 16) >> 2;
+        fin[c].mid = (code[o] + code[p]) * 0.5f;
+        fin[c].w = p | (o << 8) | ((p < (unsigned)c ? 1u : 0u) << 16);
+    }
+}
+static fin_t g_fin[7][257];
+static int g_book = 0;
+#pragma omp threadprivate(g_book)
+
 static unsigned lut_search(const float* code, const uint32_t* br, float x) {
     unsigned cm = ((to_bits(x) & 0x7fffffffu) >> 19) - (unsigned)Q8_MIN_KEY;
     cm = cm < (unsigned)Q8_MAG_CELLS ? cm : 0u;
@@ -86,12 +100,9 @@ static unsigned lut_search(const float* code, const uint32_t* br, float x) {
     const unsigned hi = b >> 16;
     while (c < hi && code[c] < x) ++c;
     c = (x == x) ? c : 0u;
-    const uint32_t po = g_po[c];
-    const char* cb = (const char*)code;
-    const unsigned p4 = po & 0xffffu, o4 = po >> 16;
-    const float midpoint = (*(const float*)(cb + o4) + *(const float*)(cb + p4)) * 0.5f;
-    const int move = (p4 < 4u * c) ? (x > midpoint) : (x < midpoint);
-    return (move ? o4 : p4) >> 2;
+    const fin_t f = g_fin[g_book][c];
+    const int move = (f.w >> 16) ? (x > f.mid) : (x < f.mid);
+    return move ? ((f.w >> 8) & 0xffu) : (f.w & 0xffu);
 }
 
 static int cmpf(const void* a, const void* b) {
@@ -130,7 +141,7 @@ int main(void) {
     books[6][0] = -1.0f; books[6][1] = -0.5f; books[6][254] = 0.5f; books[6][255] = 1.0f;
     books[6][100] = -1e-42f; books[6][101] = -0.0f; books[6][102] = 0.0f; books[6][103] = 1e-42f;
     qsort(books[6], 256, sizeof(float), cmpf);
-    for (int b = 0; b < 7; ++b) build_bracket(books[b], br[b]);
+    for (int b = 0; b < 7; ++b) { build_bracket(books[b], br[b]); build_final(books[b], g_fin[b]); }
 
     const float bound = 1.0f + 9.5367431640625e-07f; /* 1 + 2^-20 */
     int bad_total = 0;
@@ -138,6 +149,7 @@ int main(void) {
         long long bad = 0, checked = 0;
 #pragma omp parallel for schedule(static) reduction(+ : bad, checked)
         for (long long bits = 0; bits < (1LL << 32); ++bits) {
+            g_book = b;
             float x = from_bits((uint32_t)bits);
             if (!isnan(x) && fabsf(x) > bound) continue;
             ++checked;

@@ -109,6 +109,26 @@ def time_shapes(shapes):
 ROLES = ["x_issue", "mma_xfull", "mma_issued", "dec_cfull", "dec_math", "dec_empty", "dec_arrived", "mma_afull", "epi_begin", "epi_end"]
 
 
+def trace_lite(shape, mt, sp=1):
+    """Only four landmarks per tile (no per-stage stores): the undisturbed duration of the main loop and the epilogue."""
+    M, N, K = shape
+    p = make_problem(M, N, K, "nf4", "bf16")
+    os.environ["BNB_B200_TRACE_LITE"] = "1"
+    tr = torch.zeros(2 * 10 * 256, dtype=torch.int64, device="cuda")
+    run_pair(p, mt, sp)
+    run_pair(p, mt, sp, trace=tr)
+    os.environ["BNB_B200_TRACE_LITE"] = "0"
+    nat.check()
+    t = tr.cpu().numpy().reshape(2, 10, 256)
+    first, last_issued, acc, epi_end = t[0][1][0], t[0][2].max(), t[0][8][0], t[0][9][0]
+    ns = t[0][9][41] - t[0][9][40]
+    cyc = epi_end - first
+    nst = (K // 64) // (2 if sp == 2 else 1)
+    print(f"lite {M}x{N}x{K} mt={mt} sp={sp}: main loop {last_issued - first} cycles = {(last_issued - first) / max(nst, 1):.0f} per a-stage "
+          f"({nst} stages); last issue -> accumulator ready {acc - last_issued}; epilogue {epi_end - acc}; "
+          f"{cyc} cycles in {ns} ns = {cyc / max(ns, 1):.3f} GHz", flush=True)
+
+
 def trace(shape, mt):
     M, N, K = shape
     p = make_problem(M, N, K, "nf4", "bf16")
@@ -151,6 +171,13 @@ if __name__ == "__main__":
     if not args or "time" in args:
         time_shapes(shapes or [(4096, 4096, 4096), (4096, 11008, 4096), (4096, 4096, 11008), (2048, 14336, 4096),
                                (1024, 4096, 4096), (512, 4096, 4096), (8192, 8192, 8192)])
+    if not args or "lite" in args:
+        for mt in (128, 256, 384):
+            trace_lite((shapes or [(4096, 4096, 4096)])[0], mt, 1)
+        # a split tile (every tile split two ways; small enough for the fixed workspace)
+        for mt in (256, 384):
+            trace_lite((1024, 4096, 4096), mt, 1)
+            trace_lite((1024, 4096, 4096), mt, 2)
     if not args or "trace" in args:
         for xl in ("0",):
             os.environ["BNB_B200_PAIR_XLOCAL"] = xl

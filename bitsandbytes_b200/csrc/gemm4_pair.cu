@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     if (warp == 0) {
         // ================================================================== activation producer
-        if (lane == 0) {
+        // (elect.sync, not `lane == 0`: ptxas then knows the region is single-threaded and keeps the TMA / MMA operands
+        // in uniform registers instead of wrapping every instruction in an ELECT + R2UR loop -- measured: ~94 cycles
+        // per tcgen05.mma and ~800 per stage with the loop, profiles/r02_pair_trace.md)
+        if (ptx::elect_one()) {
             const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
             int s = 0;
             uint32_t ph = 0;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 18) {
         // ================================================================== code producer
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             const int ncs = (nst + 1) >> 1;
             int cs = 0;
             uint32_t ph = 0;
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // later, which the rings absorb), and the barrier of stage i+1 is probed (one non-blocking try_wait) before
         // the last MMAs of stage i -- the operands are ready long before, the probe succeeds and its latency hides
         // under the queued MMAs; only a failed probe falls back to a blocking wait.
-        if (leader && lane == 0) {
+        if (leader && ptx::elect_one()) {
             constexpr uint32_t idesc =
                 ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
             constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 ptx::fence_proxy_async_smem();
                 // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-                if (quarter == 2 && lane == 0) {  // warp 2 + 4 grp (the first warp of the group)
+                if (quarter == 2 && ptx::elect_one()) {  // warp 2 + 4 grp (the first warp of the group)
                     if (m0 + col0 < p.M) {
                         for (int d = 0; d <= p.n_peers; ++d)
                             ptx::tma_store_2d(&omaps.m[d], tile + col0 * kTileN, n0, m0 + col0);

@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
+        // (elect.sync instead of `lane == 0`: a region ptxas KNOWS to be single-threaded keeps TMA / MMA operands in
+        // uniform registers; with `lane == 0` every tcgen05.mma sits in an ELECT + R2UR loop, ~94 cycles each)
+        if (ptx::elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nst; ++i) {
@@ -183,14 +185,24 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        // ================================================================== MMA issuer
-        constexpr uint32_t idesc = ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/128, /*N=*/MT);
-        int s = 0;
-        uint32_t ph = 0;
-        for (int i = 0; i < nst; ++i) {
-            ptx::mbar_wait(&full[s], ph);
-            ptx::tc_fence_after();
-            if (lane == 0) {
+        // ================================================================== MMA issuer (one elected thread)
+        // The commit that releases stage i-1 follows the second MMA of stage i, and the barrier of stage i+1 is
+        // probed before the last MMAs of stage i (see gemm4_pair.cu): nothing but MMAs between two stages.
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/128, /*N=*/MT);
+            int s = 0, ps = 0;
+            uint32_t ph = 0;
+            ptx::mbar_wait(&full[0], 0);
+            for (int i = 0; i < nst; ++i) {
+                ptx::tc_fence_after();
+                int ns = s + 1;
+                uint32_t nph = ph;
+                if (ns == kStages) {
+                    ns = 0;
+                    nph ^= 1u;
+                }
+                const bool more = i + 1 < nst;
+                bool ok = false;
                 const uint32_t xs = ptx::smem_u32(sx + s * kXStageBytes);
                 const uint64_t bdesc0 = ptx::make_sw128_kmajor_desc(xs);
                 const uint64_t bdesc1 = ptx::make_sw128_kmajor_desc(xs + kXSubBytes);
@@ -200,16 +212,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     // K advances by 16 elements: +8 TMEM columns for A, +32 B (2 x 16 B) inside a sub-tile
                     ptx::mma_f16_ts(tmem_base, a_tmem + 8 * j, (j < 4 ? bdesc0 : bdesc1) + 2 * (j & 3), idesc,
                                     (i | j) != 0 ? 1u : 0u);
+                    if (j == 1 && i > 0) ptx::tc_commit(&empty[ps]);
+                    if (j == 6 && more) ok = ptx::mbar_try_wait(&full[ns], nph);
                 }
-                ptx::tc_commit(&empty[s]);
-                if (i == nst - 1) ptx::tc_commit(acc_full);
+                if (more && !ok) ptx::mbar_wait(&full[ns], nph);
+                ps = s;
+                s = ns;
+                ph = nph;
             }
-            __syncwarp();
-            if (++s == kStages) {
-                s = 0;
-                ph ^= 1u;
-            }
+            ptx::tc_commit(&empty[ps]);
+            ptx::tc_commit(acc_full);
         }
+        __syncwarp();
     } else {
         // ================================================================== decode warps
         const int dw = warp - 2;          // 0..15

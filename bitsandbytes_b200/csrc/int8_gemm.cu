@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
+        // (elect.sync rather than `lane == 0`: a region ptxas knows to be single-threaded keeps the TMA / MMA operands
+        // in uniform registers; with `lane == 0` every instruction is wrapped in an ELECT + R2UR loop)
+        if (ptx::elect_one()) {
             uint32_t it = 0;
             for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters) {
                 const int n0 = (pt % p.n_tiles) * kI8TileN;
@@ -185,47 +187,67 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             }
         }
     } else if (warp == 1) {
-        // ================================================================== MMA issuer
-        // kind::i8: D = S32 (2), A/B = signed int8 (1); UMMA K = 32 bytes
-        constexpr uint32_t idesc = ptx::make_idesc(2, 1, 1, PAIR ? 2 * kI8TileM : kI8TileM, kI8TileN);
-        uint32_t it = 0, tcount = 0;
-        // pair mode: only the leader issues; its instructions drive both SMs
-        for (int pt = (!PAIR || rank == 0) ? cluster_id : p.pair_tiles; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
-            const uint32_t acc = tcount & 1u;
-            ptx::mbar_wait_bounded(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);  // epilogue has drained this accumulator
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * kI8TileN;
-            for (int i = 0; i < p.kblocks; ++i, ++it) {
-                const int s = it % kI8Stages;
-                const uint32_t ph = (it / kI8Stages) & 1u;
-                ptx::mbar_wait_bounded(&full[s], ph, 3, (int)it, pt);
-                ptx::tc_fence_after();
-                if (lane == 0) {
+        // ================================================================== MMA issuer (one elected thread)
+        // kind::i8: D = S32 (2), A/B = signed int8 (1); UMMA K = 32 bytes.
+        // The tensor core accepts an MMA only about one instruction ahead (round 2 traces of the 4-bit pair kernel),
+        // so nothing but MMAs may sit between two stages: the commit that releases stage g-1 is issued after the
+        // second MMA of stage g (it then covers those two as well), and the barrier of stage g+1 is probed (one
+        // non-blocking try_wait) before the last MMAs of stage g; only a failed probe falls back to a blocking wait.
+        // pair mode: only the leader issues; its instructions drive both SMs.
+        if ((!PAIR || rank == 0) && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc(2, 1, 1, PAIR ? 2 * kI8TileM : kI8TileM, kI8TileN);
+            constexpr int kMmas = KSUB * (kI8BK / 32);  // 4 or 8 per stage
+            auto commit = [&](uint64_t* bar) {
+                if (PAIR) ptx::tc_commit_pair(bar, kMask);
+                else ptx::tc_commit_multicast(bar, kMask);
+            };
+            const int my_tiles = cluster_id < p.pair_tiles ? (p.pair_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+            const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.kblocks;  // stages this CTA pair runs
+            uint32_t g = 0, tcount = 0;
+            int prev_s = 0;
+            bool have_prev = false, ok = false;
+            if (total > 0) ptx::mbar_wait_bounded(&full[0], 0, 3, 0, 0);
+            for (int pt = cluster_id; pt < p.pair_tiles; pt += n_clusters, ++tcount) {
+                const uint32_t acc = tcount & 1u;
+                // the epilogue has drained this accumulator (two tiles ago)
+                ptx::mbar_wait_bounded(&tmem_empty[acc], ((tcount >> 1) & 1u) ^ 1u, 2, (int)tcount, pt);
+                const uint32_t d_tmem = tmem_base + acc * kI8TileN;
+                for (int i = 0; i < p.kblocks; ++i, ++g) {
+                    const int s = g % kI8Stages;
+                    ptx::tc_fence_after();
+                    const bool more = g + 1 < total;
+                    const int ns = (g + 1) % kI8Stages;
+                    const uint32_t nph = ((g + 1) / kI8Stages) & 1u;
+                    ok = false;
                     const uint32_t sa = ptx::smem_u32(stages + s * kI8StageBytes);
 #pragma unroll
-                    for (int u = 0; u < KSUB; ++u) {
-                        const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa + u * Cfg::kASubBytes);
-                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + Cfg::kABytes + u * Cfg::kBSubBytes);
-#pragma unroll
-                        for (int j = 0; j < kI8BK / 32; ++j) {
-                            const uint32_t accum = (i | u | j) != 0 ? 1u : 0u;
-                            if (PAIR)
-                                ptx::mma_i8_ss_pair(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, accum);
-                            else
-                                ptx::mma_i8_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, accum);
-                        }
+                    for (int q = 0; q < kMmas; ++q) {
+                        const int u = q / (kI8BK / 32), j = q % (kI8BK / 32);
+                        const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa + u * Cfg::kASubBytes) + 2 * j;
+                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sa + Cfg::kABytes + u * Cfg::kBSubBytes) + 2 * j;
+                        const uint32_t accum = (i | q) != 0 ? 1u : 0u;
+                        if (PAIR)
+                            ptx::mma_i8_ss_pair(d_tmem, adesc, bdesc, idesc, accum);
+                        else
+                            ptx::mma_i8_ss(d_tmem, adesc, bdesc, idesc, accum);
+                        if (q == 1 && have_prev) commit(&empty[prev_s]);
+                        if (q == kMmas - 2 && more) ok = ptx::mbar_try_wait(&full[ns], nph);
                     }
-                    if (PAIR) {
-                        ptx::tc_commit_pair(&empty[s], kMask);
-                        if (i == p.kblocks - 1) ptx::tc_commit_pair(&tmem_full[acc], kMask);
+                    if (i == p.kblocks - 1) {
+                        // end of a tile: release the last stage now and hand the accumulator to the epilogue
+                        commit(&empty[s]);
+                        if (PAIR) ptx::tc_commit_pair(&tmem_full[acc], kMask);
+                        else ptx::tc_commit(&tmem_full[acc]);
+                        have_prev = false;
                     } else {
-                        ptx::tc_commit_multicast(&empty[s], kMask);
-                        if (i == p.kblocks - 1) ptx::tc_commit(&tmem_full[acc]);
+                        prev_s = s;
+                        have_prev = true;
                     }
+                    if (more && !ok) ptx::mbar_wait_bounded(&full[ns], nph, 3, (int)g + 1, pt);
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ================================================================== epilogue warps 2..5
         const int quarter = warp & 3;  // TMEM lane quarter

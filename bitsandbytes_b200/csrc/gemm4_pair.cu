@@ -371,23 +371,16 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint4 q0 = *reinterpret_cast<const uint4*>(wt + ((hsel ^ sw_x) << 4));
                     const uint4 q1 = *reinterpret_cast<const uint4*>(wt + (((hsel + 1u) ^ sw_x) << 4));
 
-                    uint32_t r[32];
+                    // First half (32 codes) -> 16 registers -> TMEM while the second half is being decoded: the
+                    // tcgen05.st and its completion latency (~500 cycles per warp, measured) overlap the PRMT work.
+                    uint32_t ra[16], rb[16];
                     DecodeTable tab;
                     build_table<T, QT>(sc0, tab);
-                    decode_word(q0.x, tab, r + 0);
-                    decode_word(q0.y, tab, r + 4);
-                    decode_word(q0.z, tab, r + 8);
-                    decode_word(q0.w, tab, r + 12);
-                    if (two_scales) build_table<T, QT>(sc1, tab);
-                    decode_word(q1.x, tab, r + 16);
-                    decode_word(q1.y, tab, r + 20);
-                    decode_word(q1.z, tab, r + 24);
-                    decode_word(q1.w, tab, r + 28);
-                    // the codes are in registers (the decode consumed them): hand the code stage back
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);
+                    decode_word(q0.x, tab, ra + 0);
+                    decode_word(q0.y, tab, ra + 4);
+                    decode_word(q0.z, tab, ra + 8);
+                    decode_word(q0.w, tab, ra + 12);
                     if (tracer) trace_ev<TRACE>(p, 4, i);
-
                     // TMEM A slot s was last read by MMA(i - kNA), which commits to empty[(i - kNA) % kNX]
                     if (i >= kNA) {
                         const int q = i - kNA;
@@ -395,7 +388,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                     if (tracer) trace_ev<TRACE>(p, 5, i);
                     ptx::tc_fence_after();
-                    ptx::tmem_st_x32(tmem_base + (uint32_t(quarter * 32) << 16) + kACol0 + s * 32, r);
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kACol0 + s * 32;
+                    ptx::tmem_st_x16(taddr, ra);
+                    if (two_scales) build_table<T, QT>(sc1, tab);
+                    decode_word(q1.x, tab, rb + 0);
+                    decode_word(q1.y, tab, rb + 4);
+                    decode_word(q1.z, tab, rb + 8);
+                    decode_word(q1.w, tab, rb + 12);
+                    // the codes are in registers (the decode consumed them): hand the code stage back
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);
+                    ptx::tmem_st_x16(taddr + 16, rb);
                     ptx::tmem_wait_st();
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -461,15 +464,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                 T* tile = reinterpret_cast<T*>(sx);
 #pragma unroll 1
                 for (int c = 0; c < kColsPerWarp; c += 32) {
+                    // the other split's partial first, all 32 loads in flight together (issued one by one behind the
+                    // shared-memory stores below they cost an L2 round trip EACH: ~50 k cycles per tile, measured)
+                    float ov[32];
+#pragma unroll
+                    for (int t = 0; t < 32; ++t)
+                        ov[t] = other != nullptr ? __ldcg(other + (col0 + c + t) * kTileN + row) : 0.f;
                     uint32_t v[32];
                     ptx::tmem_ld_x32(lane_addr + col0 + c, v);
                     ptx::tmem_wait_ld();
 #pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        float f = __uint_as_float(v[t]);
-                        if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);
-                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(f + bias_v);
-                    }
+                    for (int t = 0; t < 32; ++t)
+                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(__uint_as_float(v[t]) + ov[t] + bias_v);
                 }
                 ptx::fence_proxy_async_smem();
                 // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const int m = m0 + col0 + c + t;
                         if (n_ok && m < p.M) {
                             float f = __uint_as_float(v[t]);
-                            if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);
+                            if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);  // (rare path: unaligned ldc)
                             const T val = DT<T>::from_f32(f + bias_v);
                             const long long idx = (long long)m * p.ldc + n;
                             outp[idx] = val;
@@ -643,8 +649,8 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     if (force_splits > 0) {
         splits = clamp(force_splits);
         tiles_main = splits > 1 ? 0 : tiles;
-        if (force_splits >= 100) {  // 100 + s: split only the partial last wave (the production rule), s ways
-            splits = clamp(force_splits - 100);
+        if (force_splits >= 100) {  // 100 + s: split only the partial last wave, when the production rule would
+            splits = (rem > 0 && rem * 2 <= P) ? clamp(force_splits - 100) : 1;
             tiles_main = splits > 1 ? tiles - rem : tiles;
         }
     } else if (rem > 0 && rem * 2 <= P) {

@@ -111,12 +111,14 @@ template <int MT> struct PairCfg {
     // activation ring (shared memory), decoupled from the A ring: as deep as the budget allows, because the
     // L2 -> SM path answers a tile load only after ~3000 cycles under load (measured) and the bytes in flight
     // per SM set the ingest rate
-    static constexpr int kNX = MT == 384 ? 6 : (MT == 256 ? 9 : 12);
+    static constexpr int kNX = MT == 384 ? 6 : 8;
+    static constexpr int kUnroll = MT == 384 ? 12 : 8;       // lcm(kNX, kNA): the MMA loop is unrolled over one ring period
     static constexpr uint32_t kACol0 = MT;                   // D: [0, MT); A slot s: MT + 32 s
     static constexpr size_t kSmemBytes = 1024 + size_t(kNX) * kXStageBytes + size_t(kNC) * kCodeStageBytes + 1024;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(size_t(kNX) * kXStageBytes >= size_t(MT) * 256, "the output tile is staged in the activation ring");
     static_assert(kSubBytes % 1024 == 0, "128-byte swizzle atoms");
+    static_assert(kUnroll % kNX == 0 && kUnroll % kNA == 0, "unroll period");
 };
 
 template <bool TRACE> __device__ __forceinline__ void trace_ev(const PairParams& p, int role, int i, bool landmark = false) {
@@ -270,27 +272,18 @@ __global__ void __launch_bounds__(kThreads, 1)
             constexpr uint32_t idesc =
                 ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
             constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
-            int s = 0, xs = 0, pxs = 0;
-            uint32_t xph = 0;
-            ptx::mbar_wait_bounded(&full[0], 0, 4, 0);
-            for (int i = 0; i < nst; ++i) {
+            // One a-stage.  `xs`, `nxs` (activation / barrier slots of this and the next stage), `pxs` (previous) and
+            // `s` (TMEM A slot) are compile-time constants in the unrolled main loop below: the single issuing thread
+            // then executes nothing but the tcgen05 instructions, one commit and one probe per stage.  (With run-time
+            // slot indices the loop body was ~45 dependent instructions, five of them R2UR: ~650 cycles per stage,
+            // measured, against 512 cycles of MMA.)
+            auto stage = [&](int i, int xs, int nxs, int pxs, int s, uint32_t nxph, bool more) {
                 trace_ev<TRACE>(p, 1, i, i == 0);
                 if (i == 0) trace_ns<TRACE>(p, 9, 40);
                 ptx::tc_fence_after();
-                int nxs = xs + 1;
-                uint32_t nxph = xph;
-                if (nxs == kNX) {
-                    nxs = 0;
-                    nxph ^= 1u;
-                }
-                const bool more = i + 1 < nst;
                 bool ok = false;
                 const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
                 const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
-                // TRACE builds: per-instruction issue times of a-stages 24 and 25 (role 9, entries 1..)
-                const bool micro = TRACE && (i == 24 || i == 25);
-                int mslot = 1 + (i - 24) * 16;
-                if (micro) trace_ev<TRACE>(p, 9, mslot++);
 #pragma unroll
                 for (int j = 0; j < kMmas; ++j) {
                     const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
@@ -298,25 +291,32 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
                     ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
                                          (i | k) != 0 ? 1u : 0u);
-                    if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                    if (j == 1 && i > 0) {
-                        ptx::tc_commit_pair(&empty[pxs], 0x3);  // stage i-1 (and the two MMAs above) retired -> slots free
-                        if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                    }
-                    if (j == kMmas - 2 && more) {
-                        ok = ptx::mbar_try_wait(&full[nxs], nxph);
-                        if (micro) trace_ev<TRACE>(p, 9, mslot++);
-                    }
+                    // stage i-1 (and the two MMAs above) retired -> its slots are free
+                    if (j == 1 && i > 0) ptx::tc_commit_pair(&empty[pxs], 0x3);
+                    if (j == kMmas - 2 && more) ok = ptx::mbar_try_wait(&full[nxs], nxph);
                 }
                 trace_ev<TRACE>(p, 2, i, i == nst - 1);
-                if (more && !ok) ptx::mbar_wait_bounded(&full[nxs], nxph, 4, i + 1);
+                if (more && !ok) ptx::mbar_wait_bounded_cold(&full[nxs], nxph, 4, i + 1);
                 trace_ev<TRACE>(p, 7, i);
-                pxs = xs;
-                xs = nxs;
-                xph = nxph;
-                if (++s == kNA) s = 0;
+            };
+            constexpr int kU = Cfg::kUnroll;  // ring period: a multiple of kNX and of kNA
+            ptx::mbar_wait_bounded(&full[0], 0, 4, 0);
+            int i = 0;
+            for (; i + kU <= nst; i += kU) {
+                const uint32_t par = (uint32_t)(i / kNX) & 1u;  // parity of the activation ring at the body's start
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int xs = u % kNX, nxs = (u + 1) % kNX, pxs = (u + kNX - 1) % kNX, s = u % kNA;
+                    const uint32_t nxph = par ^ (uint32_t)(((u + 1) / kNX) & 1);
+                    stage(i + u, xs, nxs, pxs, s, nxph, u + 1 < kU ? true : (i + kU < nst));
+                }
             }
-            ptx::tc_commit_pair(&empty[pxs], 0x3);
+            // remaining stages (fewer than a ring period): run-time slot indices
+            for (; i < nst; ++i) {
+                const int xs = i % kNX, nxs = (i + 1) % kNX, pxs = (i + kNX - 1) % kNX, s = i % kNA;
+                stage(i, xs, nxs, pxs, s, (uint32_t)((i + 1) / kNX) & 1u, i + 1 < nst);
+            }
+            ptx::tc_commit_pair(&empty[(nst - 1) % kNX], 0x3);
             ptx::tc_commit_pair(acc_full, 0x3);
         }
         __syncwarp();
@@ -704,6 +704,13 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
     if (n_peers < 0 || n_peers > 7) return false;
 
     int MT = mt_override;
+    if (MT == 0) {
+        static const int env_mt = [] {
+            const char* e = getenv("BNB_B200_PAIR_MT");  // developer override (profiling): 128 | 256 | 384
+            return e ? atoi(e) : 0;
+        }();
+        if (env_mt == 128 || env_mt == 256 || env_mt == 384) MT = env_mt;
+    }
     if (MT == 0) {
         if (M < 512) return false;  // the one-CTA kernel (with its split-K) serves the small token counts
         // Pick the token tile by the modelled time: rounds x (cycles per a-stage) (+ the non-overlapped

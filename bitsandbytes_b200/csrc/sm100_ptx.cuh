@@ -84,6 +84,12 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     }
 }
 
+// Out-of-line variant for hot loops that have already probed the barrier once: keeps the (large) polling / reporting
+// code out of the unrolled instruction stream of the MMA-issuing thread.
+static __device__ __noinline__ void mbar_wait_bounded_cold(uint64_t* bar, uint32_t parity, int tag, int a) {
+    mbar_wait_bounded(bar, parity, tag, a);
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

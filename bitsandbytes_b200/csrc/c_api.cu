@@ -342,8 +342,8 @@ int cbnb_b200_gemm_4bit_multi_out(const void* A, const uint8_t* B, const float* 
 
 // Developer / test entry: the CTA-pair kernel of gemm4_pair.cu with an explicit token tile (mt = 128 | 256 |
 // 384, 0 = automatic), a forced K split (0 = the production rule, s = every tile split s ways, 100 + s = only
-// the partial last wave) and an optional event trace (device buffer of 2 * 10 * 256 int64 clock values of
-// cluster 0; NULL = the production build).  Returns 0, or 100 when the shape is not served by that kernel.
+// the partial last wave) and an optional event trace (device buffer of 2 * 10 * 256 + 4 * 1024 int64: clock values of
+// cluster 0, then {start ns, end ns, SM, prologue cycles} per cluster; NULL = the production build).  Returns 0, or 100 when the shape is not served by that kernel.
 int cbnb_b200_gemm_4bit_pair(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                              const float* absmax_code, const float* absmax_offset, void* out, const void* bias, int M,
                              int N, int K, int ldc, int blocksize, int quant_type, int dtype, int mt, int force_splits,

@@ -138,6 +138,21 @@ template <bool TRACE> __device__ __forceinline__ void trace_ns(const PairParams&
     }
 }
 
+// per-cluster timeline (TRACE builds): [kTraceTimeline + 4 cid + {0: start ns, 1: end ns, 2: SM id, 3: prologue cycles}]
+constexpr int kTraceTimeline = 2 * kTraceRoles * kTraceStages;
+template <bool TRACE> __device__ __forceinline__ void trace_cluster(const PairParams& p, int slot, long long v = -1) {
+    if constexpr (TRACE) {
+        if (p.trace != nullptr && p.trace_lite && (blockIdx.x >> 1) < 1024) {
+            if (v < 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                v = (long long)t;
+            }
+            p.trace[kTraceTimeline + 4 * (blockIdx.x >> 1) + slot] = v;
+        }
+    }
+}
+
 template <typename T, int QT, int MT, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm4_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -170,6 +185,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = ptx::cluster_ctarank();
     const bool leader = cta_rank == 0;
+    long long t_entry = 0;
+    if constexpr (TRACE) {
+        t_entry = clock64();
+        if (threadIdx.x == 32 && leader) {
+            trace_cluster<TRACE>(p, 0);
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace_cluster<TRACE>(p, 2, (long long)smid);
+        }
+    }
 
     // cluster -> (tile, K split)
     const int cid = blockIdx.x >> 1;
@@ -200,12 +225,24 @@ __global__ void __launch_bounds__(kThreads, 1)
             ptx::mbar_init(&full[s], 9);
             ptx::mbar_init(&empty[s], 1);
         }
+        ptx::mbar_init(acc_full, 1);
+        ptx::fence_barrier_init();
+    }
+    // The code ring is CTA-local (its barriers are never touched by the peer), so its producer initialises it and
+    // starts the first kNC loads BEFORE the cluster rendezvous: their ~3000-cycle L2 latency then overlaps the
+    // TMEM allocation and the cluster barrier instead of following them.
+    const int ncs = (nst + 1) >> 1;
+    const int ncs_early = ncs < kNC ? ncs : kNC;
+    if (warp == 18 && ptx::elect_one()) {
         for (int s = 0; s < kNC; ++s) {
             ptx::mbar_init(&c_full[s], 1);
             ptx::mbar_init(&c_empty[s], 8);  // the 2 x 4 decode warps that read a code stage
         }
-        ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
+        for (int j = 0; j < ncs_early; ++j) {
+            ptx::mbar_arrive_expect_tx(&c_full[j], kCodeStageBytes);
+            ptx::tma_load_2d(sw + j * kCodeStageBytes, &tmap_w, &c_full[j], ((st_begin + 2 * j) * kAK) / 2, n0);
+        }
     }
     if (warp == 1) {
         ptx::tmem_alloc_pair<512>(tmem_slot);
@@ -244,10 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else if (warp == 18) {
         // ================================================================== code producer
         if (ptx::elect_one()) {
-            const int ncs = (nst + 1) >> 1;
-            int cs = 0;
-            uint32_t ph = 0;
-            for (int j = 0; j < ncs; ++j) {
+            int cs = ncs_early % kNC;
+            uint32_t ph = (uint32_t)(ncs_early / kNC) & 1u;
+            for (int j = ncs_early; j < ncs; ++j) {
                 ptx::mbar_wait_bounded(&c_empty[cs], ph ^ 1u, 2, j);
                 ptx::mbar_arrive_expect_tx(&c_full[cs], kCodeStageBytes);
                 // bytes [k/2, k/2 + 64) of rows n0 .. n0+127 (rows past N / bytes past K/2: zero-filled)
@@ -280,6 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             auto stage = [&](int i, int xs, int nxs, int pxs, int s, uint32_t nxph, bool more) {
                 trace_ev<TRACE>(p, 1, i, i == 0);
                 if (i == 0) trace_ns<TRACE>(p, 9, 40);
+                if constexpr (TRACE) {
+                    if (i == 0) trace_cluster<TRACE>(p, 3, clock64() - t_entry);
+                }
                 ptx::tc_fence_after();
                 bool ok = false;
                 const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
@@ -462,20 +501,30 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (p.tma_out) {
                 // tile in shared memory: [MT token rows][128 features] of T, 256 B per row, in the idle activation ring
                 T* tile = reinterpret_cast<T*>(sx);
-#pragma unroll 1
-                for (int c = 0; c < kColsPerWarp; c += 32) {
-                    // the other split's partial first, all 32 loads in flight together (issued one by one behind the
-                    // shared-memory stores below they cost an L2 round trip EACH: ~50 k cycles per tile, measured)
-                    float ov[32];
+                // The other split's partial is fetched one chunk AHEAD (32 loads in flight while the previous chunk is
+                // converted and stored): issued one by one behind the shared-memory stores the loads cost an L2 round
+                // trip EACH (~50 k cycles per tile, measured), batched but not prefetched ~2.5 k per chunk.
+                constexpr int kChunks = kColsPerWarp / 32;
+                float ov[2][32];
+                auto load_other = [&](float* dst, int c) {
 #pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        ov[t] = other != nullptr ? __ldcg(other + (col0 + c + t) * kTileN + row) : 0.f;
+                    for (int t = 0; t < 32; ++t) dst[t] = __ldcg(other + (col0 + c + t) * kTileN + row);
+                };
+                if (other != nullptr) load_other(ov[0], 0);
+#pragma unroll
+                for (int ci = 0; ci < kChunks; ++ci) {
+                    const int c = ci * 32;
                     uint32_t v[32];
                     ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                    if (other != nullptr && ci + 1 < kChunks) load_other(ov[(ci + 1) & 1], c + 32);
                     ptx::tmem_wait_ld();
+                    if (other != nullptr) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + ov[ci & 1][t]);
+                    }
 #pragma unroll
                     for (int t = 0; t < 32; ++t)
-                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(__uint_as_float(v[t]) + ov[t] + bias_v);
+                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
                 }
                 ptx::fence_proxy_async_smem();
                 // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
@@ -521,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_pair(tmem_base, 512);
+        if (leader && lane == 0) trace_cluster<TRACE>(p, 1);
     }
 }
 
@@ -691,7 +741,7 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
 
 // Large-M route of the 4-bit GEMM.  Returns false when the shape is not served here (the caller falls back
 // to the one-CTA kernel of gemm4_tc.cu).  `mt_override` (0 = automatic) and `force_splits` are for the
-// probes / tests; `trace` (device buffer of 2 * kTraceRoles * kTraceStages int64) selects the traced build.
+// probes / tests; `trace` (device buffer of 2 * kTraceRoles * kTraceStages + 4 * 1024 int64) selects the traced build.
 template <typename T>
 bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                        const float* absmax_code, const float* absmax_offset, T* out, const T* bias, int M, int N, int K,

@@ -157,7 +157,7 @@ void cbnb_b200_gemm_4bit_force_path(int path);
 
 /* Developer / test entry for the CTA-pair (cta_group::2) large-M kernel (csrc/gemm4_pair.cu): explicit token
  * tile mt (128 | 256 | 384; 0 = automatic), forced K split (0 = production rule; s = every tile s ways;
- * 100 + s = only the partial last wave), optional event trace (device buffer of 2*10*256 int64 clocks, or NULL).
+ * 100 + s = only the partial last wave), optional event trace (device buffer of 2*10*256 + 4*1024 int64, or NULL).
  * Returns 0, or 100 when the shape is not served by that kernel. */
 int cbnb_b200_gemm_4bit_pair(const void* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset, void* out, const void* bias, int M, int N, int K, int ldc, int blocksize, int quant_type, int dtype, int mt, int force_splits, long long* trace, bnb_stream_t stream);
 

@@ -64,7 +64,7 @@ def eq():
                 bad = int((a.view(torch.int16) != b.view(torch.int16)).sum())
                 # split K changes the fp32 summation order: compare within a few ulp instead of bit-equal
                 # (sp = 0 is the production rule, which splits the partial last wave of large problems)
-                if bad and (sp != 0 or M >= 2048):
+                if bad and (sp != 0 or M * N >= 2048 * 2048):
                     rel = float((a.float() - b.float()).norm() / a.float().norm())
                     good = rel < 2e-3 and not torch.isnan(b.float()).any()
                     print(f"eq {M}x{N}x{K} {qt} {dt} {kw} mt={mt} splits={sp}: {'ok' if good else 'MISMATCH'} "
@@ -92,12 +92,9 @@ def time_shapes(shapes):
         parts = []
         t, m = timeit(lambda: run_old_nosync(p, out), iters=15)
         parts.append(f"one-CTA {t:.1f} us ({fl/t/1e6:.0f} TF)")
-        for xl in ("0",):
-            os.environ["BNB_B200_PAIR_XLOCAL"] = xl
-            for mt, sp in ((256, 0), (256, 1), (384, 0), (384, 1)):
-                t, m = timeit(lambda: run_pair(p, mt, sp, out=out, sync=False), iters=15)
-                parts.append(f"pair xl={xl} mt={mt} sp={sp} {t:.1f} us ({fl/t/1e6:.0f} TF, min {m:.1f})")
-        os.environ["BNB_B200_PAIR_XLOCAL"] = "0"
+        for mt, sp in ((256, 0), (256, 1), (384, 0), (384, 1)):
+            t, m = timeit(lambda: run_pair(p, mt, sp, out=out, sync=False), iters=15)
+            parts.append(f"pair mt={mt} sp={sp} {t:.1f} us ({fl/t/1e6:.0f} TF, min {m:.1f})")
         # cuBLAS bf16 for context
         W = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
         t, m = timeit(lambda: torch.matmul(p["x"], W.t(), out=out), iters=15)
@@ -114,12 +111,39 @@ def trace_lite(shape, mt, sp=1):
     M, N, K = shape
     p = make_problem(M, N, K, "nf4", "bf16")
     os.environ["BNB_B200_TRACE_LITE"] = "1"
-    tr = torch.zeros(2 * 10 * 256, dtype=torch.int64, device="cuda")
+    tr = torch.zeros(2 * 10 * 256 + 4 * 1024, dtype=torch.int64, device="cuda")
     run_pair(p, mt, sp)
     run_pair(p, mt, sp, trace=tr)
     os.environ["BNB_B200_TRACE_LITE"] = "0"
     nat.check()
-    t = tr.cpu().numpy().reshape(2, 10, 256)
+    full = tr.cpu().numpy()
+    t = full[:2 * 10 * 256].reshape(2, 10, 256)
+    tl = full[2 * 10 * 256:].reshape(1024, 4)
+    tl = tl[tl[:, 0] > 0]
+    if len(tl):
+        t0 = tl[:, 0].min()
+        st, en, sm, pro = tl[:, 0] - t0, tl[:, 1] - t0, tl[:, 2], tl[:, 3]
+        dur = en - st
+        order = np.argsort(st)
+        print(f"timeline {M}x{N}x{K} mt={mt} sp={sp}: {len(tl)} clusters on {len(set(sm.tolist()))} SMs; kernel span {en.max()} ns; "
+              f"cluster duration median {np.median(dur):.0f} ns (p10 {np.percentile(dur,10):.0f}, p90 {np.percentile(dur,90):.0f}); "
+              f"prologue (entry -> first MMA) median {np.median(pro):.0f} cycles (p90 {np.percentile(pro,90):.0f})")
+        # per SM: the chain of clusters it ran, and the gaps between them
+        gaps, chains = [], {}
+        for i in order:
+            chains.setdefault(int(sm[i]), []).append(i)
+        for k, c in chains.items():
+            for a, b in zip(c[:-1], c[1:]):
+                gaps.append(st[b] - en[a])
+        if gaps:
+            print(f"   same-SM gap between consecutive clusters: median {np.median(gaps):.0f} ns (p90 {np.percentile(gaps,90):.0f}); "
+                  f"first start spread {np.percentile(st[order[:len(chains)]],90):.0f} ns; last end - median of last-round ends "
+                  f"{en.max() - np.median([en[c[-1]] for c in chains.values()]):.0f} ns")
+        nround = max(len(c) for c in chains.values())
+        for r in range(nround):
+            ids = [c[r] for c in chains.values() if len(c) > r]
+            print(f"   round {r}: {len(ids)} clusters, start {np.median(st[ids]):.0f}, end median {np.median(en[ids]):.0f} max {en[ids].max()}, "
+                  f"duration median {np.median(dur[ids]):.0f} ns")
     first, last_issued, acc, epi_end = t[0][1][0], t[0][2].max(), t[0][8][0], t[0][9][0]
     ns = t[0][9][41] - t[0][9][40]
     cyc = epi_end - first
@@ -179,10 +203,6 @@ if __name__ == "__main__":
             trace_lite((1024, 4096, 4096), mt, 1)
             trace_lite((1024, 4096, 4096), mt, 2)
     if not args or "trace" in args:
-        for xl in ("0",):
-            os.environ["BNB_B200_PAIR_XLOCAL"] = xl
-            print(f"===== BNB_B200_PAIR_XLOCAL={xl}")
-            for mt in (256, 384):
-                trace((shapes or [(4096, 4096, 4096)])[0], mt)
-        os.environ["BNB_B200_PAIR_XLOCAL"] = "0"
+        for mt in (256, 384):
+            trace((shapes or [(4096, 4096, 4096)])[0], mt)
     print("done ok=", ok)

@@ -92,7 +92,8 @@ struct PairParams {
     int ka_total;        // a-stages in K
     int n_pairs;         // 256-feature tiles along N
     int tiles_total;
-    int tiles_main;      // tiles [0, tiles_main) are computed by one cluster each, the rest by `splits_tail`
+    int tiles_main;      // tiles [0, tiles_main) are whole items, the rest is cut into `splits_tail` K ranges
+    int n_items;         // tiles_main + (tiles_total - tiles_main) * splits_tail
     int splits_tail;
 };
 
@@ -115,8 +116,8 @@ template <int MT> struct PairCfg {
     static constexpr int kUnroll = MT == 384 ? 12 : 8;       // lcm(kNX, kNA): the MMA loop is unrolled over one ring period
     static constexpr uint32_t kACol0 = MT;                   // D: [0, MT); A slot s: MT + 32 s
     static constexpr size_t kSmemBytes = 1024 + size_t(kNX) * kXStageBytes + size_t(kNC) * kCodeStageBytes + 1024;
+    static_assert(4 * kXStageBytes == MT * 256 && kNX > 4, "the output tile is staged in four slots of the activation ring");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-    static_assert(size_t(kNX) * kXStageBytes >= size_t(MT) * 256, "the output tile is staged in the activation ring");
     static_assert(kSubBytes % 1024 == 0, "128-byte swizzle atoms");
     static_assert(kUnroll % kNX == 0 && kUnroll % kNA == 0, "unroll period");
 };
@@ -138,19 +139,60 @@ template <bool TRACE> __device__ __forceinline__ void trace_ns(const PairParams&
     }
 }
 
-// per-cluster timeline (TRACE builds): [kTraceTimeline + 4 cid + {0: start ns, 1: end ns, 2: SM id, 3: prologue cycles}]
+// per-cluster timeline (TRACE builds, lite mode):
+//   [kTraceTimeline + 8 cid + {0: start ns, 1: end ns, 2: SM id, 3: cycles entry -> first MMA, 4..7: end ns of item 0..3}]
 constexpr int kTraceTimeline = 2 * kTraceRoles * kTraceStages;
+constexpr int kTimelineSlots = 8;
 template <bool TRACE> __device__ __forceinline__ void trace_cluster(const PairParams& p, int slot, long long v = -1) {
     if constexpr (TRACE) {
-        if (p.trace != nullptr && p.trace_lite && (blockIdx.x >> 1) < 1024) {
+        if (p.trace != nullptr && p.trace_lite && (blockIdx.x >> 1) < 512 && slot < kTimelineSlots) {
             if (v < 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                 v = (long long)t;
             }
-            p.trace[kTraceTimeline + 4 * (blockIdx.x >> 1) + slot] = v;
+            p.trace[kTraceTimeline + kTimelineSlots * (blockIdx.x >> 1) + slot] = v;
         }
     }
+}
+
+// One unit of work of a cluster: an output tile (256 features x MT tokens), or one K half of a tile of the
+// partial last round.
+struct PairItem {
+    int tile, split, splits;
+    int n0, m0;          // this CTA's first feature / the tile's first token
+    int st_begin, nst;   // K range in a-stages (nst >= 1: the host only splits when every split gets work)
+};
+template <int MT> __device__ __forceinline__ PairItem pair_item(const PairParams& p, int w, uint32_t cta_rank) {
+    PairItem it;
+    it.split = 0;
+    it.splits = 1;
+    if (w < p.tiles_main) {
+        it.tile = w;
+    } else {
+        const int r = w - p.tiles_main;
+        it.splits = p.splits_tail;
+        it.tile = p.tiles_main + r / it.splits;
+        it.split = r - (r / it.splits) * it.splits;
+    }
+    it.n0 = (it.tile % p.n_pairs) * (2 * kTileN) + (int)cta_rank * kTileN;
+    it.m0 = (it.tile / p.n_pairs) * MT;
+    // boundaries on even a-stages (= whole code stages)
+    int per = (p.ka_total + it.splits - 1) / it.splits;
+    per += per & 1;
+    it.st_begin = it.split * per;
+    int st_end = it.st_begin + per;
+    if (st_end > p.ka_total) st_end = p.ka_total;
+    it.nst = st_end - it.st_begin;
+    return it;
+}
+// Every item restarts its rings at slot 0 (so the MMA loop can be unrolled with compile-time slots); the
+// mbarrier phases of course keep counting.  `base` holds, per slot, the parity of the uses completed by the
+// earlier items: an item of n stages uses slot x (n - x + R - 1) / R times.
+template <int R> __device__ __forceinline__ uint32_t ring_base_after(uint32_t base, int n) {
+    const int fullr = n / R, rem = n - fullr * R;
+    if (fullr & 1) base ^= (1u << R) - 1u;
+    return base ^ ((1u << rem) - 1u);
 }
 
 template <typename T, int QT, int MT, bool TRACE>
@@ -162,24 +204,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr int kNX = Cfg::kNX;
     constexpr int kXStageBytes = Cfg::kXStageBytes;
     constexpr uint32_t kACol0 = Cfg::kACol0;
+    static_assert(kNA == 4 || (kNA == 8 && kNX == 8), "decode-side ring bookkeeping");
 
+    // Everything in shared memory is addressed by 32-bit shared-space addresses off ONE base (sm100_ptx.cuh, "_a"
+    // helpers): no generic pointers, no cvta, no 64-bit address arithmetic in the hot loops.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sx = smem;                                   // [kNX][kNSub][kBoxRows x 128 B]
-    uint8_t* sw = smem + kNX * kXStageBytes;              // [kNC][128 x 64 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sw + kNC * kCodeStageBytes);
+    const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sx = sbase;                                  // [kNX][kNSub][kBoxRows x 128 B]
+    const uint32_t sw = sx + kNX * kXStageBytes;                // [kNC][128 x 64 B]
+    // the output tile ([MT token rows][128 features] of T = 4 activation slots) is staged in the TOP four slots of
+    // the activation ring: the producer may refill the lower ones for the next item while the epilogue runs
+    const uint32_t so = sx + (kNX - 4) * kXStageBytes;
     // ONE barrier pair per a-stage, indexed by the activation slot i % kNX (the TMEM A slot is i % kNA):
     //   full[i % kNX]   the stage's activation bytes (both CTAs) + the 8 decode warps (both CTAs) -> MMA  (leader's)
     //   empty[i % kNX]  MMA(i) has retired -> the activation producer (slot reusable at stage i + kNX) AND the
     //                   decode warps (TMEM A slot reusable at stage i + kNA <= i + kNX)
     // so the MMA thread pays one wait and one commit per stage while the activation ring is deeper than the A ring.
-    uint64_t* full = bars;                  // [kNX]
-    uint64_t* empty = bars + kNX;           // [kNX]
-    uint64_t* c_full = empty + kNX;         // [kNC]
-    uint64_t* c_empty = c_full + kNC;       // [kNC]
-    uint64_t* acc_full = c_empty + kNC;     // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    const uint32_t full = sw + kNC * kCodeStageBytes;           // [kNX]
+    const uint32_t empty = full + 8 * kNX;                      // [kNX]
+    const uint32_t c_full = empty + 8 * kNX;                    // [kNC]
+    const uint32_t c_empty = c_full + 8 * kNC;                  // [kNC]
+    const uint32_t acc_full = c_empty + 8 * kNC;   // accumulators of the item complete -> the decode warps' epilogue
+    const uint32_t acc_empty = acc_full + 8;       // accumulators read out (32 warps of both CTAs) -> MMA of the next item (leader's)
+    const uint32_t tile_free = acc_empty + 8;      // the 4 decode groups' bulk stores have read the staged tile -> activation producer
+    const uint32_t tmem_slot = tile_free + 8;
+    const uint32_t s_flag = tmem_slot + 4;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -196,62 +245,52 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     }
 
-    // cluster -> (tile, K split)
+    // Persistent: cluster c works on the items c, c + #clusters, ... (whole tiles first, the K halves of the
+    // partial last round at the end).  Only the first item pays the launch, the TMEM allocation, the cluster
+    // rendezvous and the cold pipeline (~10 k cycles, measured: profiles/r02_pair_trace.md); on the later ones
+    // the producers are already ahead when the epilogue of the previous item ends.
     const int cid = blockIdx.x >> 1;
-    int tile, split = 0, splits = 1;
-    if (cid < p.tiles_main) {
-        tile = cid;
-    } else {
-        const int r = cid - p.tiles_main;
-        splits = p.splits_tail;
-        tile = p.tiles_main + r / splits;
-        split = r - (r / splits) * splits;
-    }
-    const int n0 = (tile % p.n_pairs) * (2 * kTileN) + (int)cta_rank * kTileN;  // this CTA's 128 features
-    const int m0 = (tile / p.n_pairs) * MT;
-    // K range of this split, in a-stages; boundaries on even a-stages (= whole code stages)
-    int per = (p.ka_total + splits - 1) / splits;
-    per += per & 1;
-    const int st_begin = split * per;
-    int st_end = st_begin + per;
-    if (st_end > p.ka_total) st_end = p.ka_total;
-    const int nst = st_end - st_begin;  // >= 1: the host only splits when every split gets work
+    const int ncl = gridDim.x >> 1;
+    const PairItem first = pair_item<MT>(p, cid, cta_rank);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kNX; ++s) {
             // leader: its producer's expect_tx arrival (bytes of both CTAs) + the 4 decode warps of each CTA
-            ptx::mbar_init(&full[s], 9);
-            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init_a(full + 8 * s, 9);
+            ptx::mbar_init_a(empty + 8 * s, 1);
         }
-        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init_a(acc_full, 1);
+        ptx::mbar_init_a(acc_empty, 2 * kDecodeWarps);
+        ptx::mbar_init_a(tile_free, 4);
         ptx::fence_barrier_init();
     }
     // The code ring is CTA-local (its barriers are never touched by the peer), so its producer initialises it and
     // starts the first kNC loads BEFORE the cluster rendezvous: their ~3000-cycle L2 latency then overlaps the
     // TMEM allocation and the cluster barrier instead of following them.
-    const int ncs = (nst + 1) >> 1;
-    const int ncs_early = ncs < kNC ? ncs : kNC;
+    const int ncs_first = (first.nst + 1) >> 1;
+    const int ncs_early = ncs_first < kNC ? ncs_first : kNC;
     if (warp == 18 && ptx::elect_one()) {
         for (int s = 0; s < kNC; ++s) {
-            ptx::mbar_init(&c_full[s], 1);
-            ptx::mbar_init(&c_empty[s], 8);  // the 2 x 4 decode warps that read a code stage
+            ptx::mbar_init_a(c_full + 8 * s, 1);
+            ptx::mbar_init_a(c_empty + 8 * s, 8);  // the 2 x 4 decode warps that read a code stage
         }
         ptx::fence_barrier_init();
         for (int j = 0; j < ncs_early; ++j) {
-            ptx::mbar_arrive_expect_tx(&c_full[j], kCodeStageBytes);
-            ptx::tma_load_2d(sw + j * kCodeStageBytes, &tmap_w, &c_full[j], ((st_begin + 2 * j) * kAK) / 2, n0);
+            ptx::mbar_arrive_expect_tx_a(c_full + 8 * j, kCodeStageBytes);
+            ptx::tma_load_2d_a(sw + j * kCodeStageBytes, &tmap_w, c_full + 8 * j, ((first.st_begin + 2 * j) * kAK) / 2,
+                               first.n0);
         }
     }
     if (warp == 1) {
-        ptx::tmem_alloc_pair<512>(tmem_slot);
+        ptx::tmem_alloc_pair_a<512>(tmem_slot);
         ptx::tmem_relinquish_pair();
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = ptx::lds_u32(tmem_slot);
 
     if (warp == 0) {
         // ================================================================== activation producer
@@ -259,39 +298,61 @@ __global__ void __launch_bounds__(kThreads, 1)
         // in uniform registers instead of wrapping every instruction in an ELECT + R2UR loop -- measured: ~94 cycles
         // per tcgen05.mma and ~800 per stage with the loop, profiles/r02_pair_trace.md)
         if (ptx::elect_one()) {
-            const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < nst; ++i) {
-                ptx::mbar_wait_bounded(&empty[s], ph ^ 1u, 1, i);  // MMA(i - kNX) has retired
-                trace_ev<TRACE>(p, 0, i);
-                const int k0 = (st_begin + i) * kAK;
-                if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * kXStageBytes);
-                uint8_t* dst = sx + s * kXStageBytes;
+            const uint32_t lead_full0 = ptx::mapa_u32(full, 0);
+            uint32_t base = 0;
+            int item = 0;
+            for (int w = cid; w < p.n_items; w += ncl, ++item) {
+                const PairItem it = pair_item<MT>(p, w, cta_rank);
+                int s = 0;
+                uint32_t ph = 0;
+                bool tile_pending = item > 0;  // the previous item's output tile may still sit in slots kNX-4 .. kNX-1
+                for (int i = 0; i < it.nst; ++i) {
+                    if (tile_pending && s >= kNX - 4) {
+                        ptx::mbar_wait_a(tile_free, (uint32_t)(item - 1) & 1u, 9, item);
+                        tile_pending = false;
+                    }
+                    // the previous use of the slot (this item's stage i - kNX, or the previous item's) has retired
+                    ptx::mbar_wait_a(empty + 8 * s, ((base >> s) & 1u) ^ ph ^ 1u, 1, i);
+                    if (w == cid) trace_ev<TRACE>(p, 0, i);
+                    const int k0 = (it.st_begin + i) * kAK;
+                    if (leader) ptx::mbar_arrive_expect_tx_a(full + 8 * s, 2 * kXStageBytes);
+                    const uint32_t dst = sx + s * kXStageBytes;
 #pragma unroll
-                for (int sub = 0; sub < Cfg::kNSub; ++sub)
-                    ptx::tma_load_2d_pair(dst + sub * Cfg::kSubBytes, &tmap_x, lead_full0 + 8u * s, k0,
-                                          m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
-                if (++s == kNX) {
-                    s = 0;
-                    ph ^= 1u;
+                    for (int sub = 0; sub < Cfg::kNSub; ++sub)
+                        ptx::tma_load_2d_pair_a(dst + sub * Cfg::kSubBytes, &tmap_x, lead_full0 + 8u * s, k0,
+                                                it.m0 + sub * Cfg::kUmmaN + (int)cta_rank * Cfg::kBoxRows);
+                    if (++s == kNX) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
+                // (every phase of tile_free is observed, also by an item too short to reach the staging slots)
+                if (tile_pending) ptx::mbar_wait_a(tile_free, (uint32_t)(item - 1) & 1u, 9, item);
+                base = ring_base_after<kNX>(base, it.nst);
             }
         }
     } else if (warp == 18) {
         // ================================================================== code producer
         if (ptx::elect_one()) {
-            int cs = ncs_early % kNC;
-            uint32_t ph = (uint32_t)(ncs_early / kNC) & 1u;
-            for (int j = ncs_early; j < ncs; ++j) {
-                ptx::mbar_wait_bounded(&c_empty[cs], ph ^ 1u, 2, j);
-                ptx::mbar_arrive_expect_tx(&c_full[cs], kCodeStageBytes);
-                // bytes [k/2, k/2 + 64) of rows n0 .. n0+127 (rows past N / bytes past K/2: zero-filled)
-                ptx::tma_load_2d(sw + cs * kCodeStageBytes, &tmap_w, &c_full[cs], ((st_begin + 2 * j) * kAK) / 2, n0);
-                if (++cs == kNC) {
-                    cs = 0;
-                    ph ^= 1u;
+            uint32_t base = 0;
+            for (int w = cid; w < p.n_items; w += ncl) {
+                const PairItem it = pair_item<MT>(p, w, cta_rank);
+                const int ncs = (it.nst + 1) >> 1;
+                const int j0 = w == cid ? ncs_early : 0;  // the first item's first loads are already in flight
+                int cs = j0 % kNC;
+                uint32_t ph = (uint32_t)(j0 / kNC) & 1u;
+                for (int j = j0; j < ncs; ++j) {
+                    ptx::mbar_wait_a(c_empty + 8 * cs, ((base >> cs) & 1u) ^ ph ^ 1u, 2, j);
+                    ptx::mbar_arrive_expect_tx_a(c_full + 8 * cs, kCodeStageBytes);
+                    // bytes [k/2, k/2 + 64) of rows n0 .. n0+127 (rows past N / bytes past K/2: zero-filled)
+                    ptx::tma_load_2d_a(sw + cs * kCodeStageBytes, &tmap_w, c_full + 8 * cs,
+                                       ((it.st_begin + 2 * j) * kAK) / 2, it.n0);
+                    if (++cs == kNC) {
+                        cs = 0;
+                        ph ^= 1u;
+                    }
                 }
+                base = ring_base_after<kNC>(base, ncs);
             }
         }
     } else if (warp == 1) {
@@ -308,203 +369,265 @@ __global__ void __launch_bounds__(kThreads, 1)
             constexpr uint32_t idesc =
                 ptx::make_idesc(/*D=F32*/ 1, TcFmt<T>::kFmt, TcFmt<T>::kFmt, /*M=*/256, /*N=*/Cfg::kUmmaN);
             constexpr int kMmas = (kAK / 16) * Cfg::kNSub;  // 4 or 8 per a-stage
-            // One a-stage.  `xs`, `nxs` (activation / barrier slots of this and the next stage), `pxs` (previous) and
-            // `s` (TMEM A slot) are compile-time constants in the unrolled main loop below: the single issuing thread
-            // then executes nothing but the tcgen05 instructions, one commit and one probe per stage.  (With run-time
-            // slot indices the loop body was ~45 dependent instructions, five of them R2UR: ~650 cycles per stage,
-            // measured, against 512 cycles of MMA.)
-            auto stage = [&](int i, int xs, int nxs, int pxs, int s, uint32_t nxph, bool more) {
-                trace_ev<TRACE>(p, 1, i, i == 0);
-                if (i == 0) trace_ns<TRACE>(p, 9, 40);
-                if constexpr (TRACE) {
-                    if (i == 0) trace_cluster<TRACE>(p, 3, clock64() - t_entry);
-                }
-                ptx::tc_fence_after();
-                bool ok = false;
-                const uint32_t xa = ptx::smem_u32(sx + xs * kXStageBytes);
-                const uint32_t a_tmem = tmem_base + kACol0 + s * 32;
+            constexpr int kU = Cfg::kUnroll;                // ring period: a multiple of kNX and of kNA
+            uint32_t base = 0;
+            int item = 0;
+            for (int w = cid; w < p.n_items; w += ncl, ++item) {
+                const PairItem it = pair_item<MT>(p, w, cta_rank);
+                const int nst = it.nst;
+                const bool tr = TRACE && item == 0;
+                // One a-stage.  `xs`, `nxs` (activation / barrier slots of this and the next stage), `pxs` (previous)
+                // and `s` (TMEM A slot) are compile-time constants in the unrolled main loop below: the single issuing
+                // thread then executes nothing but the tcgen05 instructions, one commit and one probe per stage.  (With
+                // run-time slot indices the loop body was ~45 dependent instructions, five of them R2UR: ~650 cycles
+                // per stage, measured, against 512 cycles of MMA.)
+                auto stage = [&](int i, int xs, int nxs, int pxs, int s, uint32_t nxph, bool more) {
+                    if (tr) trace_ev<TRACE>(p, 1, i, i == 0);
+                    if constexpr (TRACE) {
+                        if (tr && i == 0) {
+                            trace_ns<TRACE>(p, 9, 40);
+                            trace_cluster<TRACE>(p, 3, clock64() - t_entry);
+                        }
+                    }
+                    ptx::tc_fence_after();
+                    bool ok = false;
+                    // (opaque to the optimiser: otherwise the 96 loop-invariant 64-bit descriptors of the unrolled ring
+                    // period are hoisted into vector registers, spilled, and fed back through ~20 R2UR per stage)
+                    uint32_t xa = sx + xs * kXStageBytes;
+                    uint32_t a_tmem = tmem_base + kACol0 + s * 32;
+                    asm volatile("" : "+r"(xa), "+r"(a_tmem));
 #pragma unroll
-                for (int j = 0; j < kMmas; ++j) {
-                    const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
-                    // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
-                    const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
-                    ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
-                                         (i | k) != 0 ? 1u : 0u);
-                    // stage i-1 (and the two MMAs above) retired -> its slots are free
-                    if (j == 1 && i > 0) ptx::tc_commit_pair(&empty[pxs], 0x3);
-                    if (j == kMmas - 2 && more) ok = ptx::mbar_try_wait(&full[nxs], nxph);
-                }
-                trace_ev<TRACE>(p, 2, i, i == nst - 1);
-                if (more && !ok) ptx::mbar_wait_bounded_cold(&full[nxs], nxph, 4, i + 1);
-                trace_ev<TRACE>(p, 7, i);
-            };
-            constexpr int kU = Cfg::kUnroll;  // ring period: a multiple of kNX and of kNA
-            ptx::mbar_wait_bounded(&full[0], 0, 4, 0);
-            int i = 0;
-            for (; i + kU <= nst; i += kU) {
-                const uint32_t par = (uint32_t)(i / kNX) & 1u;  // parity of the activation ring at the body's start
+                    for (int j = 0; j < kMmas; ++j) {
+                        const int k = j / Cfg::kNSub, sub = j % Cfg::kNSub;
+                        // K advances by 16 elements: +8 TMEM columns of A, +32 B inside the 128-byte swizzle row
+                        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(xa + sub * Cfg::kSubBytes) + 2 * k;
+                        ptx::mma_f16_ts_pair(tmem_base + sub * Cfg::kUmmaN, a_tmem + 8 * k, bdesc, idesc,
+                                             (i | k) != 0 ? 1u : 0u);
+                        // stage i-1 (and the two MMAs above) retired -> its slots are free
+                        if (j == 1 && i > 0) ptx::tc_commit_pair_a(empty + 8 * pxs, 0x3);
+                        if (j == kMmas - 2 && more) ok = ptx::mbar_try_wait_a(full + 8 * nxs, nxph);
+                    }
+                    if (tr) trace_ev<TRACE>(p, 2, i, i == nst - 1);
+                    if (more && !ok) ptx::mbar_wait_slow_a(full + 8 * nxs, nxph, 4, i + 1);
+                    if (tr) trace_ev<TRACE>(p, 7, i);
+                };
+                // the accumulators of the previous item have been read out by both CTAs' epilogues
+                if (item > 0) ptx::mbar_wait_a(acc_empty, (uint32_t)(item - 1) & 1u, 8, item);
+                ptx::mbar_wait_a(full, base & 1u, 4, 0);
+                int i = 0;
+                for (; i + kU <= nst; i += kU) {
+                    const uint32_t par = (uint32_t)(i / kNX) & 1u;  // parity of the activation ring at the body's start
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int xs = u % kNX, nxs = (u + 1) % kNX, pxs = (u + kNX - 1) % kNX, s = u % kNA;
-                    const uint32_t nxph = par ^ (uint32_t)(((u + 1) / kNX) & 1);
-                    stage(i + u, xs, nxs, pxs, s, nxph, u + 1 < kU ? true : (i + kU < nst));
+                    for (int u = 0; u < kU; ++u) {
+                        const int xs = u % kNX, nxs = (u + 1) % kNX, pxs = (u + kNX - 1) % kNX, s = u % kNA;
+                        const uint32_t nxph = par ^ (uint32_t)(((u + 1) / kNX) & 1) ^ ((base >> nxs) & 1u);
+                        stage(i + u, xs, nxs, pxs, s, nxph, u + 1 < kU ? true : (i + kU < nst));
+                    }
                 }
+                // remaining stages (fewer than a ring period): run-time slot indices
+                for (; i < nst; ++i) {
+                    const int xs = i % kNX, nxs = (i + 1) % kNX, pxs = (i + kNX - 1) % kNX, s = i % kNA;
+                    stage(i, xs, nxs, pxs, s, ((uint32_t)((i + 1) / kNX) & 1u) ^ ((base >> nxs) & 1u), i + 1 < nst);
+                }
+                ptx::tc_commit_pair_a(empty + 8 * ((nst - 1) % kNX), 0x3);
+                ptx::tc_commit_pair_a(acc_full, 0x3);
+                base = ring_base_after<kNX>(base, nst);
             }
-            // remaining stages (fewer than a ring period): run-time slot indices
-            for (; i < nst; ++i) {
-                const int xs = i % kNX, nxs = (i + 1) % kNX, pxs = (i + kNX - 1) % kNX, s = i % kNA;
-                stage(i, xs, nxs, pxs, s, (uint32_t)((i + 1) / kNX) & 1u, i + 1 < nst);
-            }
-            ptx::tc_commit_pair(&empty[(nst - 1) % kNX], 0x3);
-            ptx::tc_commit_pair(acc_full, 0x3);
         }
         __syncwarp();
     } else {
         // ================================================================== decode warps
+        // The decode is ISSUE bound: each scheduler hosts one warp of every group, so a scheduler issues one warp's
+        // whole stage per a-stage (~500 instructions of which 270 are the PRMT decode and the table build).  Hence
+        // no div/mod by the ring sizes (incremental slots), no generic addresses, no branches around the arrives.
         const int dw = warp - 2;        // 0..15
         const int quarter = warp & 3;   // TMEM lane quarter this warp may touch
         const int grp = dw >> 2;        // decodes the a-stages i with i % 4 == grp
         const int row = quarter * 32 + lane;
-        const int n = n0 + row;
-        const bool n_ok = n < p.N;
-        const long long e_row = (long long)(n_ok ? n : 0) * p.K;
         ScaleSrc sc{p.absmax, p.absmax_8bit, p.absmax_code, p.absmax_offset ? __ldg(p.absmax_offset) : 0.0f};
         const bool two_scales = p.log2_bs == 5;
-        const uint32_t sw_row = (uint32_t)row * 64u;
-        const uint32_t sw_x = (uint32_t)((row >> 1) & 3);  // 64-byte swizzle: chunk c of row r sits at c ^ ((r>>1)&3)
-        const bool tracer = TRACE && quarter == 0 && lane == 0;
-        const uint32_t lead_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+        // 64-byte swizzle: 16-byte chunk c of code row r sits at c ^ ((r >> 1) & 3); a stage reads chunks {0,1} or {2,3}
+        const uint32_t code_off = sw + (uint32_t)row * 64u + (uint32_t)(((row >> 1) & 3) << 4);
+        const bool tracer0 = TRACE && quarter == 0 && lane == 0;
+        // the leader's barriers through shared::cluster addresses: the same (relaxed) arrive from both CTAs
+        const uint32_t lead_full0 = ptx::mapa_u32(full, 0);
+        const uint32_t lead_acc_empty = ptx::mapa_u32(acc_empty, 0);
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+        // this warp in the epilogue: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4) (= tokens)
+        constexpr int kColsPerWarp = MT / 4;  // 32, 64 or 96
+        constexpr int kChunks = kColsPerWarp / 32;
+        const int col0 = grp * kColsPerWarp;
+        T* outp = reinterpret_cast<T*>(p.out);
 
+        // per-thread register ring of scales (the stages this group owns, kScaleDepth ahead)
         float wsc[kScaleDepth][2];
-        auto fetch = [&](int j, int t) {
+        PairItem it = first;
+        long long e0 = 0;   // element index of (this thread's row, first k of the item); -1: row past N
+        auto item_base = [&](const PairItem& q) {
+            const int n = q.n0 + row;
+            e0 = n < p.N ? (long long)n * p.K + (long long)q.st_begin * kAK : -1;
+        };
+        auto fetch = [&](const PairItem& q, int j, int t) {
             wsc[j][0] = wsc[j][1] = 0.f;
             const int i = 4 * t + grp;
-            if (i < nst && n_ok) {
-                const long long e = e_row + (long long)(st_begin + i) * kAK;
+            if (i < q.nst && e0 >= 0) {
+                const long long e = e0 + (long long)i * kAK;
                 wsc[j][0] = sc.load(e >> p.log2_bs);
                 if (two_scales) wsc[j][1] = sc.load((e + 32) >> p.log2_bs);
             }
         };
+        item_base(it);
 #pragma unroll
-        for (int j = 0; j < kScaleDepth; ++j) fetch(j, j);
+        for (int j = 0; j < kScaleDepth; ++j) fetch(it, j, j);
 
-        const int cnt = (nst - grp + 3) >> 2;  // a-stages this group owns
-        for (int t0 = 0; t0 < cnt; t0 += kScaleDepth) {
+        uint32_t base_x = 0, base_c = 0;
+        int item = 0;
+        for (int w = cid; w < p.n_items; w += ncl, ++item) {
+            const int nst = it.nst;
+            const bool tracer = tracer0 && item == 0;
+            const int cnt = (nst - grp + 3) >> 2;  // a-stages this group owns
+            // ring positions of stage i = grp + 4 t, advanced incrementally
+            int xs = grp;                 // i % kNX (kNX > 4 > grp)
+            uint32_t xph = 0;             // (i / kNX) & 1
+            int pxs = 0;                  // slot / parity of stage i - 4 (kNA == 4: the stage whose MMA frees A slot)
+            uint32_t pxph = 0;
+            int cs = grp >> 1;            // (i / 2) % kNC
+            uint32_t cph = 0;             // (i / 2 / kNC) & 1
+            int i = grp;
+            for (int t0 = 0; t0 < cnt; t0 += kScaleDepth) {
 #pragma unroll
-            for (int j = 0; j < kScaleDepth; ++j) {
-                const int t = t0 + j;
-                if (t < cnt) {
-                    const int i = 4 * t + grp;
-                    const int s = i % kNA;   // TMEM A slot
-                    const int xs = i % kNX;  // barrier (activation) slot of this stage
-                    const int cj = i >> 1;
-                    const int cs = cj % kNC;
-                    const uint32_t cph = (uint32_t)(cj / kNC) & 1u;
-                    const uint32_t hsel = (uint32_t)(i & 1) * 2u;  // which 32 bytes of the 64-byte code row
-                    const float sc0 = wsc[j][0], sc1 = wsc[j][1];
-                    fetch(j, t + kScaleDepth);
+                for (int j = 0; j < kScaleDepth; ++j) {
+                    const int t = t0 + j;
+                    if (t < cnt) {
+                        const float sc0 = wsc[j][0], sc1 = wsc[j][1];
+                        fetch(it, j, t + kScaleDepth);
 
-                    ptx::mbar_wait_bounded(&c_full[cs], cph, 5, i);
-                    if (tracer) trace_ev<TRACE>(p, 3, i);
-                    const uint8_t* wt = sw + cs * kCodeStageBytes + sw_row;
-                    const uint4 q0 = *reinterpret_cast<const uint4*>(wt + ((hsel ^ sw_x) << 4));
-                    const uint4 q1 = *reinterpret_cast<const uint4*>(wt + (((hsel + 1u) ^ sw_x) << 4));
+                        ptx::mbar_wait_a(c_full + 8 * cs, cph ^ ((base_c >> cs) & 1u), 5, i);
+                        if (tracer) trace_ev<TRACE>(p, 3, i);
+                        // which 32 bytes of the 64-byte code row: chunks {0,1} (even stage) or {2,3} (odd)
+                        const uint32_t wt = (code_off + cs * kCodeStageBytes) ^ ((uint32_t)(i & 1) << 5);
+                        const uint4 q0 = ptx::lds128(wt);
+                        const uint4 q1 = ptx::lds128(wt ^ 16u);
 
-                    // First half (32 codes) -> 16 registers -> TMEM while the second half is being decoded: the
-                    // tcgen05.st and its completion latency (~500 cycles per warp, measured) overlap the PRMT work.
-                    uint32_t ra[16], rb[16];
-                    DecodeTable tab;
-                    build_table<T, QT>(sc0, tab);
-                    decode_word(q0.x, tab, ra + 0);
-                    decode_word(q0.y, tab, ra + 4);
-                    decode_word(q0.z, tab, ra + 8);
-                    decode_word(q0.w, tab, ra + 12);
-                    if (tracer) trace_ev<TRACE>(p, 4, i);
-                    // TMEM A slot s was last read by MMA(i - kNA), which commits to empty[(i - kNA) % kNX]
-                    if (i >= kNA) {
-                        const int q = i - kNA;
-                        ptx::mbar_wait_bounded(&empty[q % kNX], (uint32_t)(q / kNX) & 1u, 6, i);
+                        // First half (32 codes) -> 16 registers -> TMEM while the second half is being decoded: the
+                        // tcgen05.st and its completion latency (~500 cycles per warp, measured) overlap the PRMT work.
+                        uint32_t ra[16], rb[16];
+                        DecodeTable tab;
+                        build_table<T, QT>(sc0, tab);
+                        decode_word(q0.x, tab, ra + 0);
+                        decode_word(q0.y, tab, ra + 4);
+                        decode_word(q0.z, tab, ra + 8);
+                        decode_word(q0.w, tab, ra + 12);
+                        if (tracer) trace_ev<TRACE>(p, 4, i);
+                        // TMEM A slot i % kNA was last read by MMA(i - kNA), which commits to empty[(i - kNA) % kNX]; the
+                        // first kNA stages of an item follow the epilogue of the previous one (everything retired)
+                        if (i >= kNA) {
+                            if constexpr (kNA == 4)
+                                ptx::mbar_wait_a(empty + 8 * pxs, pxph ^ ((base_x >> pxs) & 1u), 6, i);
+                            else  // kNA == kNX == 8: same slot, one ring turn earlier
+                                ptx::mbar_wait_a(empty + 8 * xs, xph ^ 1u ^ ((base_x >> xs) & 1u), 6, i);
+                        }
+                        if (tracer) trace_ev<TRACE>(p, 5, i);
+                        ptx::tc_fence_after();
+                        const uint32_t taddr = lane_addr + kACol0 + (uint32_t)(kNA == 4 ? grp : (i & 7)) * 32u;
+                        ptx::tmem_st_x16(taddr, ra);
+                        if (two_scales) build_table<T, QT>(sc1, tab);
+                        decode_word(q1.x, tab, rb + 0);
+                        decode_word(q1.y, tab, rb + 4);
+                        decode_word(q1.z, tab, rb + 8);
+                        decode_word(q1.w, tab, rb + 12);
+                        // the codes are in registers (the decode consumed them): hand the code stage back.  An item with
+                        // an odd number of a-stages leaves the second half of its last code stage unused: the group that
+                        // decodes the last stage arrives for the missing one too (the producer reuses the ring in the
+                        // next item).
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::mbar_arrive_a(c_empty + 8 * cs);
+                            if (i == nst - 1 && (i & 1) == 0) ptx::mbar_arrive_a(c_empty + 8 * cs);
+                        }
+                        ptx::tmem_st_x16(taddr + 16, rb);
+                        ptx::tmem_wait_st();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        // "this warp's 32 rows of the A slot are in TMEM": the payload is tensor memory, completed by
+                        // wait::st above -- no generic-proxy data to release, hence the relaxed (cluster) arrive
+                        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_full0 + 8u * xs);
+                        if (tracer) trace_ev<TRACE>(p, 6, i);
+
+                        // next owned stage: i + 4
+                        pxs = xs;
+                        pxph = xph;
+                        i += 4;
+                        xs += 4;
+                        if (xs >= kNX) {
+                            xs -= kNX;
+                            xph ^= 1u;
+                        }
+                        cs += 2;
+                        if (cs >= kNC) {
+                            cs -= kNC;
+                            cph ^= 1u;
+                        }
                     }
-                    if (tracer) trace_ev<TRACE>(p, 5, i);
-                    ptx::tc_fence_after();
-                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kACol0 + s * 32;
-                    ptx::tmem_st_x16(taddr, ra);
-                    if (two_scales) build_table<T, QT>(sc1, tab);
-                    decode_word(q1.x, tab, rb + 0);
-                    decode_word(q1.y, tab, rb + 4);
-                    decode_word(q1.z, tab, rb + 8);
-                    decode_word(q1.w, tab, rb + 12);
-                    // the codes are in registers (the decode consumed them): hand the code stage back
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);
-                    ptx::tmem_st_x16(taddr + 16, rb);
-                    ptx::tmem_wait_st();
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        // "this warp's 32 rows of A slot s are in TMEM": the payload is tensor memory, completed by
-                        // wait::st above -- no generic-proxy data to release, hence the relaxed remote arrive
-                        if (leader)
-                            ptx::mbar_arrive(&full[xs]);
-                        else
-                            ptx::mbar_arrive_cluster_relaxed(lead_full0 + 8u * xs);
-                    }
-                    if (tracer) trace_ev<TRACE>(p, 6, i);
                 }
             }
-        }
 
-        // ================================================================== epilogue
-        ptx::mbar_wait_bounded(acc_full, 0, 7);
-        ptx::tc_fence_after();
-        if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0, true);
-
-        // this warp: lanes [quarter*32, +32) (= output features), columns [grp*MT/4, +MT/4) (= tokens)
-        constexpr int kColsPerWarp = MT / 4;  // 32, 64 or 96
-        const int col0 = grp * kColsPerWarp;
-        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-        T* outp = reinterpret_cast<T*>(p.out);
-        float bias_v = 0.f;
-        if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
-
-        bool finish = true;            // this CTA writes the output tile (false: first split to arrive)
-        const float* other = nullptr;  // the other split's fp32 partial ([column][row]) to add, or NULL
-        if (splits == 2) {
-            // ---- split K: publish the fp32 partial tile ([column][row]: coalesced both ways) and count in on the
-            // (tile, CTA) counter.  The LAST of the two splits to arrive adds the other's partial to its own
-            // accumulators (still in TMEM) and writes the tile; the first one is done.  Nobody waits.
-            const int tt = (tile - p.tiles_main) * 2 + (int)cta_rank;
-            float* ws_tile = p.ws_partial + (long long)tt * 2 * (kTileN * MT);
-            float* my = ws_tile + (long long)split * (kTileN * MT);
-#pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
-                uint32_t v[32];
-                ptx::tmem_ld_x32(lane_addr + col0 + c, v);
-                ptx::tmem_wait_ld();
+            // the next item's scales travel while this item's epilogue runs
+            const PairItem cur = it;
+            if (w + ncl < p.n_items) {
+                it = pair_item<MT>(p, w + ncl, cta_rank);
+                item_base(it);
 #pragma unroll
-                for (int t = 0; t < 32; ++t) __stcg(my + (col0 + c + t) * kTileN + row, __uint_as_float(v[t]));
+                for (int j = 0; j < kScaleDepth; ++j) fetch(it, j, j);
             }
-            __threadfence();
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (threadIdx.x == 64) {
-                const int old = atomicAdd(p.ws_counter + tt, 1);
-                *s_flag = old;
-                if (old == 1) p.ws_counter[tt] = 0;  // both have arrived: reset for the next launch
-                __threadfence();
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            finish = *s_flag == 1;
-            other = ws_tile + (long long)(split ^ 1) * (kTileN * MT);
-        }
 
-        if (finish) {
-            if (p.tma_out) {
-                // tile in shared memory: [MT token rows][128 features] of T, 256 B per row, in the idle activation ring
-                T* tile = reinterpret_cast<T*>(sx);
-                // The other split's partial is fetched one chunk AHEAD (32 loads in flight while the previous chunk is
+            // ================================================================== epilogue
+            ptx::mbar_wait_a(acc_full, (uint32_t)item & 1u, 7, item);
+            ptx::tc_fence_after();
+            if (tracer && grp == 0) trace_ev<TRACE>(p, 8, 0, true);
+
+            const int n = cur.n0 + row;
+            const bool n_ok = n < p.N;
+            float bias_v = 0.f;
+            if (p.bias != nullptr && n_ok) bias_v = DT<T>::to_f32(reinterpret_cast<const T*>(p.bias)[n]);
+
+            bool finish = true;            // this CTA writes the output tile (false: first split to arrive)
+            const float* other = nullptr;  // the other split's fp32 partial ([column][row]) to add, or NULL
+            if (cur.splits == 2) {
+                // ---- split K: publish the fp32 partial tile ([column][row]: coalesced both ways) and count in on the
+                // (tile, CTA) counter.  The LAST of the two splits to arrive adds the other's partial to its own
+                // accumulators (still in TMEM) and writes the tile; the first one is done.  Nobody waits.
+                const int tt = (cur.tile - p.tiles_main) * 2 + (int)cta_rank;
+                float* ws_tile = p.ws_partial + (long long)tt * 2 * (kTileN * MT);
+                float* my = ws_tile + (long long)cur.split * (kTileN * MT);
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) __stcg(my + (col0 + c + t) * kTileN + row, __uint_as_float(v[t]));
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    const int old = atomicAdd(p.ws_counter + tt, 1);
+                    ptx::sts_u32(s_flag, (uint32_t)old);
+                    if (old == 1) p.ws_counter[tt] = 0;  // both have arrived: reset for the next launch
+                    __threadfence();
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                finish = ptx::lds_u32(s_flag) == 1u;
+                other = ws_tile + (long long)(cur.split ^ 1) * (kTileN * MT);
+            }
+
+            if (finish && p.tma_out) {
+                // tile in shared memory: [MT token rows][128 features] of T, 256 B per row; the 4 warps of this decode
+                // group own token rows [col0, col0 + MT/4) and send them with ONE bulk store per destination.  The
+                // other split's partial is fetched one chunk AHEAD (32 loads in flight while the previous chunk is
                 // converted and stored): issued one by one behind the shared-memory stores the loads cost an L2 round
-                // trip EACH (~50 k cycles per tile, measured), batched but not prefetched ~2.5 k per chunk.
-                constexpr int kChunks = kColsPerWarp / 32;
+                // trip EACH (~50 k cycles per tile, measured).
+                const uint32_t trow = so + (uint32_t)(col0 * kTileN + row) * 2u;  // (token col0, this feature)
                 float ov[2][32];
                 auto load_other = [&](float* dst, int c) {
 #pragma unroll
@@ -518,49 +641,70 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ptx::tmem_ld_x32(lane_addr + col0 + c, v);
                     if (other != nullptr && ci + 1 < kChunks) load_other(ov[(ci + 1) & 1], c + 32);
                     ptx::tmem_wait_ld();
+                    if (ci == kChunks - 1) {
+                        // accumulators read out: the MMA thread may start the next item
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_acc_empty);
+                    }
                     if (other != nullptr) {
 #pragma unroll
                         for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + ov[ci & 1][t]);
                     }
 #pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        tile[(col0 + c + t) * kTileN + row] = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
+                    for (int t = 0; t < 32; ++t) {
+                        const T val = DT<T>::from_f32(__uint_as_float(v[t]) + bias_v);
+                        ptx::sts_b16(trow + (uint32_t)(c + t) * (kTileN * 2), reinterpret_cast<const uint16_t&>(val));
+                    }
                 }
                 ptx::fence_proxy_async_smem();
-                // the 4 warps of this decode group own token rows [col0, col0 + MT/4): one bulk store per destination
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
                 if (quarter == 2 && ptx::elect_one()) {  // warp 2 + 4 grp (the first warp of the group)
-                    if (m0 + col0 < p.M) {
+                    if (cur.m0 + col0 < p.M) {
                         for (int d = 0; d <= p.n_peers; ++d)
-                            ptx::tma_store_2d(&omaps.m[d], tile + col0 * kTileN, n0, m0 + col0);
+                            ptx::tma_store_2d_a(&omaps.m[d], so + (uint32_t)(col0 * kTileN) * 2u, cur.n0, cur.m0 + col0);
                         ptx::tma_store_commit();
+                        ptx::tma_store_wait_read();  // shared memory must outlive the reads (not the global writes)
                     }
-                    ptx::tma_store_wait_read();  // shared memory must outlive the reads (not the global writes)
+                    ptx::mbar_arrive_a(tile_free);  // the activation producer may refill this group's part of the ring
                 }
             } else {
+                if (finish) {
 #pragma unroll 1
-                for (int c = 0; c < kColsPerWarp; c += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_x32(lane_addr + col0 + c, v);
-                    ptx::tmem_wait_ld();
+                    for (int c = 0; c < kColsPerWarp; c += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_x32(lane_addr + col0 + c, v);
+                        ptx::tmem_wait_ld();
 #pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        const int m = m0 + col0 + c + t;
-                        if (n_ok && m < p.M) {
-                            float f = __uint_as_float(v[t]);
-                            if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);  // (rare path: unaligned ldc)
-                            const T val = DT<T>::from_f32(f + bias_v);
-                            const long long idx = (long long)m * p.ldc + n;
-                            outp[idx] = val;
-                            for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                        for (int t = 0; t < 32; ++t) {
+                            const int m = cur.m0 + col0 + c + t;
+                            if (n_ok && m < p.M) {
+                                float f = __uint_as_float(v[t]);
+                                if (other != nullptr) f += __ldcg(other + (col0 + c + t) * kTileN + row);  // (rare path: unaligned ldc)
+                                const T val = DT<T>::from_f32(f + bias_v);
+                                const long long idx = (long long)m * p.ldc + n;
+                                outp[idx] = val;
+                                for (int r2 = 0; r2 < p.n_peers; ++r2) reinterpret_cast<T*>(p.peer_out[r2])[idx] = val;
+                            }
                         }
                     }
                 }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive_cluster_relaxed(lead_acc_empty);
+                    if (quarter == 2) ptx::mbar_arrive_a(tile_free);  // nothing staged
+                }
             }
-        }
-        if (tracer && grp == 0) {
-            trace_ev<TRACE>(p, 9, 0, true);
-            trace_ns<TRACE>(p, 9, 41);
+            if (tracer && grp == 0) {
+                trace_ev<TRACE>(p, 9, 0, true);
+                trace_ns<TRACE>(p, 9, 41);
+            }
+            if constexpr (TRACE) {
+                if (tracer0 && grp == 0 && leader) trace_cluster<TRACE>(p, 4 + item);
+            }
+            base_x = ring_base_after<kNX>(base_x, nst);
+            base_c = ring_base_after<kNC>(base_c, (nst + 1) >> 1);
         }
     }
 
@@ -722,7 +866,8 @@ bool launch_pair_mt(const T* A, PairParams& p, cudaStream_t stream, int force_sp
     }
 
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (tiles_main + split_tiles * splits), 1, 1);
+    p.n_items = tiles_main + split_tiles * splits;
+    cfg.gridDim = dim3(2 * (p.n_items < P ? p.n_items : P), 1, 1);  // persistent: one cluster per SM pair
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;

@@ -351,6 +351,100 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- 32-bit shared-space addressing
+// The same primitives on shared::cta ADDRESSES (uint32_t) instead of generic pointers.  A kernel that keeps one
+// 32-bit base and adds compile-time offsets needs no cvta, no 64-bit address arithmetic and gets LDS/STS instead of
+// generic LD/ST (measured on the CTA-pair 4-bit GEMM: ~90 fewer instructions per decode stage and warp).
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t"
+                 ".reg .pred P;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P;\n\t"
+                 "}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// the polling / time-out half of a wait, out of line: hot loops carry one probe and a (rarely taken) call
+static __device__ __noinline__ void mbar_wait_slow_a(uint32_t bar, uint32_t parity, int tag, int a) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_a(bar, parity)) {
+        if ((++spins & 0x3FFF) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > 10000000000ull) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("bnb200: mbarrier wait timed out (tag=%d block=%d warp=%d parity=%u a=%d)\n", tag,
+                           (int)blockIdx.x, (int)(threadIdx.x >> 5), parity, a);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int tag, int a = 0) {
+    if (!mbar_try_wait_a(bar, parity)) mbar_wait_slow_a(bar, parity, tag, a);
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c_inner,
+                                              int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_a(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                   int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap* m, uint32_t smem_src, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_src), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_a(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+template <int kCols> __device__ __forceinline__ void tmem_alloc_pair_a(uint32_t smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(kCols)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_b16(uint32_t a, uint16_t v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes
 // with the 128-byte swizzle (what a TMA load with CU_TENSOR_MAP_SWIZZLE_128B produces):

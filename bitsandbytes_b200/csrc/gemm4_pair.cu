@@ -908,18 +908,21 @@ bool launch_gemm4_pair(const T* A, const uint8_t* B, const float* absmax, const 
     }
     if (MT == 0) {
         if (M < 512) return false;  // the one-CTA kernel (with its split-K) serves the small token counts
-        // Pick the token tile by the modelled time: rounds x (cycles per a-stage) (+ the non-overlapped
-        // epilogue); MT=384 is MMA-bound (768 cycles per a-stage), MT=256 pays the decode (~ 600).
+        // Pick the token tile by the modelled time of the busiest cluster (cycles, measured on B200 in round 2,
+        // profiles/r02_pair_trace.md): MT = 384 runs an a-stage in ~806 cycles (the two N = 192 MMAs per k-step
+        // take 768), MT = 256 in ~656 (decode bound); an item costs ~9 k / ~7 k more for its drain, epilogue and
+        // restart, a K half ~4 k on top for the partial exchange.
         const int n_pairs = (N + 255) / 256;
         const int P = device_sm_count() / 2;
-        auto cost = [&](int mt, double stage_cycles) {
+        auto cost = [&](int mt, double stage_cycles, double item_cycles) {
             const int tiles = n_pairs * ((M + mt - 1) / mt);
             const int rem = tiles % P;
-            double rounds = tiles / P;
-            if (rem > 0) rounds += (rem * 2 <= P) ? 0.5 + 0.08 : 1.0;
-            return rounds * ((K / 64) * stage_cycles + 3000.0 + 8.0 * mt);
+            const double item = (K / 64) * stage_cycles + item_cycles;
+            double c = (tiles / P) * item;
+            if (rem > 0) c += (rem * 2 <= P && K >= 1024) ? 0.5 * (K / 64) * stage_cycles + item_cycles + 4000.0 : item;
+            return c;
         };
-        MT = cost(384, 800.0) <= cost(256, 620.0) ? 384 : 256;
+        MT = cost(384, 806.0, 9000.0) <= cost(256, 656.0, 7000.0) ? 384 : 256;
     }
     if (MT != 128 && MT != 256 && MT != 384) return false;
 

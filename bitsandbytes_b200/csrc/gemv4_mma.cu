@@ -205,8 +205,12 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
         const char* e = getenv("BNB_B200_GEMV_WARPS");
         return e ? atoi(e) : 0;
     }();
+    // Narrow layers (N <= 2048: fewer than one CTA per SM at 8 warps): 16 warps per CTA split K into single
+    // 256-wide chunks so that the whole packed weight is in flight at once (measured, 1024 x 4096, M = 1..8:
+    // 5.9-6.6 us against 6.7-7.2; wider layers lose 5-15 % with 16 warps, profiles/r02_decode_regime.md).
     int warps = ((long long)grid.x * 4 >= 12LL * device_sm_count()) ? 4 : 8;
-    if (forced_w == 4 || forced_w == 8) warps = forced_w;
+    if (K >= 16 * kGChunk && (int)grid.x <= 128) warps = 16;
+    if (forced_w == 4 || forced_w == 8 || forced_w == 16) warps = forced_w;
 #define BNB200_GEMV_MMA(QT, WV)                                                                                        \
     do {                                                                                                               \
         if (M <= 8)                                                                                                    \
@@ -218,10 +222,12 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
     } while (0)
     if (quant_type == kNF4) {
         if (warps == 4) BNB200_GEMV_MMA(kNF4, 4);
-        else BNB200_GEMV_MMA(kNF4, 8);
+        else if (warps == 8) BNB200_GEMV_MMA(kNF4, 8);
+        else BNB200_GEMV_MMA(kNF4, 16);
     } else {
         if (warps == 4) BNB200_GEMV_MMA(kFP4, 4);
-        else BNB200_GEMV_MMA(kFP4, 8);
+        else if (warps == 8) BNB200_GEMV_MMA(kFP4, 8);
+        else BNB200_GEMV_MMA(kFP4, 16);
     }
 #undef BNB200_GEMV_MMA
     BNB200_CHECK_LAUNCH("gemv4_mma");

@@ -8,7 +8,7 @@
               fused GEMM vs (bit-exact dequantize) @ x in fp32, vs the CPU oracle on a sampled sub-problem and vs
               the reference CUDA library's own fused kernel.
 * the fused outlier epilogue against an explicit chain at small ragged shapes; one process driving two devices;
-  a 2-GPU run where the fused peer-store gather == NCCL gather == single-GPU result (skipped on one GPU).
+  a 2-GPU run where the fused peer-store gather == NCCL gather (bit-exact) ~= single-GPU result (skipped on one GPU).
 """
 import os
 import subprocess
@@ -316,8 +316,14 @@ for M in (48, 1024):
     peers = PeerGather(M, N, torch.bfloat16, dev)
     fused = fused_forward(layer, x, peers).clone()
     torch.cuda.synchronize()
-    assert torch.equal(nccl, single), f"M={M}: NCCL-gathered shards differ from the single-GPU result"
-    assert torch.equal(fused, single), f"M={M}: fused peer-store gather differs from the single-GPU result"
+    # the fused exchange must be BIT-identical to the NCCL one (same kernel, same shard shapes); against the
+    # single-GPU layer the K split of the partial last round differs with the tile count, so only the fp32
+    # summation order -- at most an ulp of bf16 per element -- may differ
+    assert torch.equal(fused, nccl), f"M={M}: fused peer-store gather differs from the NCCL gather"
+    rel = float((nccl.float() - single.float()).norm() / single.float().norm())
+    assert rel < 2e-3 and not torch.isnan(nccl.float()).any(), f"M={M}: sharded result off the single-GPU one (rel {rel:.2e})"
+    worst = float((nccl.float() - single.float()).abs().max() / single.float().abs().max())
+    assert worst < 1e-2, f"M={M}: max deviation {worst:.2e}"
 dist.barrier()
 dist.destroy_process_group()
 print("TWO_GPU_OK", rank)

@@ -51,24 +51,58 @@ template <> struct WarpMma<__half> {
     }
 };
 
-// W = warps per CTA (they split K).  Codes and scales of the next chunk are prefetched into registers;
-// activations come through L1 (every CTA on an SM reads the same M x K slice).  Measured and dropped:
-// staging the activations with cp.async (slower, it bypasses L1), issuing their loads before the
-// decode, 3 or 4 CTAs per SM through a register cap -- all within noise of this version.
+// ---------------------------------------------------------------- warp-private cp.async ring
+// Decode-time shapes are latency problems: 8-30 MB must be IN FLIGHT almost at once (Little's law: ~50 KB per SM
+// at HBM latency), but a register prefetch of one chunk per warp (2 KB) holds 32 KB per SM.  Each warp therefore
+// owns a ring of kRing stages in shared memory, filled with cp.async (16 bytes per lane and row half, 4 bytes per
+// scale): a lane only ever reads back the bytes it copied itself, so `cp.async.wait_group` is all the
+// synchronisation there is -- no barrier, no __syncwarp.  ncu (profiles/r02_decode_regime.md) showed the kernel short of
+// WARPS, not of bytes in flight or issue slots (20 % of the warp slots, ALU pipe 53 %, issue 31 %): so the register
+// budget is 64 (32 resident warps per SM: decode and MMA go word by word instead of 32 codes at a time) and the ring
+// is 2 deep (32 warps x 1 stage x 2 KB = 64 KB in flight per SM while the other stage is decoded).
+constexpr int kRing = 2;
+constexpr int kRingStageBytes = 4 * 512 + 4 * 128;  // 4 code parts [32 lanes x 16 B] + 4 scale parts [32 lanes x 4 B]
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
+// W = warps per CTA (they split K in 256-wide chunks and meet in shared memory at the end).  Activations come
+// through L1 (every CTA on an SM reads the same M x K slice).  Measured and dropped: staging the activations with
+// cp.async (slower, it bypasses L1), 3 or 4 CTAs per SM through a register cap, a byte-indexed shared-memory decode
+// table (profiles/r02_decode_regime.md).
 // NT = groups of 8 tokens (1: M <= 8, 2: M <= 16): the decoded weight fragments feed NT MMAs each.
 template <typename T, int QT, int W, int NT>
-__global__ void __launch_bounds__(W * 32, 2)
+__global__ void __launch_bounds__(W * 32, 32 / W)
     gemv4_mma_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, const float* absmax,
                      const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset,
                      T* __restrict__ out, const T* __restrict__ bias, int M, int N, int K, int ldc, int log2_bs) {
     __shared__ float red[W][kGRows * 8 * NT];
+    extern __shared__ __align__(16) uint8_t ring_smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2;
     const int t = lane & 3;
     const int n0 = blockIdx.x * kGRows;
-    ScaleSrc sc{absmax, absmax_8bit, absmax_code,
-                (absmax_8bit != nullptr && absmax_offset != nullptr) ? __ldg(absmax_offset) : 0.f};
+    const bool nested = absmax_8bit != nullptr;
+    ScaleSrc sc{absmax, absmax_8bit, absmax_code, (nested && absmax_offset != nullptr) ? __ldg(absmax_offset) : 0.f};
     const bool two_scales = log2_bs == 5;  // blocksize 32: two quantisation blocks per 64 codes
     bool tok_ok[NT];                       // this lane's tokens (MMA column g of token group u)
     const T* arow[NT];
@@ -92,75 +126,110 @@ __global__ void __launch_bounds__(W * 32, 2)
 #pragma unroll
     for (int u = 0; u < NT; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f;
     const int nchunks = (K + kGChunk - 1) / kGChunk;
+    const int my_chunks = warp < nchunks ? (nchunks - warp + W - 1) / W : 0;  // chunks warp, warp + W, ...
 
-    uint4 q[2][2];
-    float s[2][2];
-    auto fetch = [&](int ch) {
-        const int kb = ch * kGChunk + 64 * t;
-        const bool live = ch < nchunks && kb < K;
+    // ring stage of this warp: code part p (0: row g lo 16 B, 1: row g hi, 2: row g+8 lo, 3: row g+8 hi) of lane l at
+    // p * 512 + 16 l; scale part p at 2048 + p * 128 + 4 l  (conflict-free both ways)
+    const uint32_t ring0 = static_cast<uint32_t>(__cvta_generic_to_shared(ring_smem)) + (uint32_t)warp * (kRing * kRingStageBytes);
+    auto issue = [&](int i) {
+        if (i < my_chunks) {
+            const int kb = (warp + W * i) * kGChunk + 64 * t;
+            const uint32_t st = ring0 + (uint32_t)(i % kRing) * kRingStageBytes;
+            if (kb < K) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            q[h][0] = q[h][1] = make_uint4(0, 0, 0, 0);
-            s[h][0] = s[h][1] = 0.f;
-            if (live && row_ok[h]) {
-                const long long e = e_row[h] + kb;
-                const uint8_t* src = B + (e >> 1);
-                q[h][0] = ldg_stream_v4(src);
-                q[h][1] = ldg_stream_v4(src + 16);
-                s[h][0] = sc.load(e >> log2_bs);
-                s[h][1] = two_scales ? sc.load((e + 32) >> log2_bs) : s[h][0];
+                for (int h = 0; h < 2; ++h) {
+                    if (row_ok[h]) {
+                        const long long e = e_row[h] + kb;
+                        const uint8_t* src = B + (e >> 1);
+                        cp_async16(st + (2 * h) * 512 + lane * 16, src);
+                        cp_async16(st + (2 * h + 1) * 512 + lane * 16, src + 16);
+                        if (!nested) {
+                            cp_async4(st + 2048 + (2 * h) * 128 + lane * 4, absmax + (e >> log2_bs));
+                            if (two_scales) cp_async4(st + 2048 + (2 * h + 1) * 128 + lane * 4, absmax + ((e + 32) >> log2_bs));
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_commit();  // (an empty group keeps the group count in step with the iteration count)
+    };
+#pragma unroll
+    for (int i = 0; i < kRing - 1; ++i) issue(i);
+
+    // double-quantised statistics are computed, not copied: one chunk ahead in registers
+    float ns[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    auto fetch_nested = [&](int i) {
+        ns[0][0] = ns[0][1] = ns[1][0] = ns[1][1] = 0.f;
+        if (nested && i < my_chunks) {
+            const int kb = (warp + W * i) * kGChunk + 64 * t;
+            if (kb < K) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (row_ok[h]) {
+                        const long long e = e_row[h] + kb;
+                        ns[h][0] = sc.load(e >> log2_bs);
+                        ns[h][1] = two_scales ? sc.load((e + 32) >> log2_bs) : ns[h][0];
+                    }
+                }
             }
         }
     };
-    fetch(warp);
+    fetch_nested(0);
 
-    for (int ch = warp; ch < nchunks; ch += W) {
-        const int kb = ch * kGChunk + 64 * t;
+    for (int i = 0; i < my_chunks; ++i) {
+        const int kb = (warp + W * i) * kGChunk + 64 * t;
         const bool k_ok = kb < K;
-        const uint4 q00 = q[0][0], q01 = q[0][1], q10 = q[1][0], q11 = q[1][1];
-        const float s00 = s[0][0], s01 = s[0][1], s10 = s[1][0], s11 = s[1][1];
-        fetch(ch + W);
+        issue(i + kRing - 1);
+        cp_async_wait<kRing - 1>();  // this lane's copies of stage i have landed
+        const uint32_t st = ring0 + (uint32_t)(i % kRing) * kRingStageBytes;
+        float sv[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            sv[h][0] = sv[h][1] = 0.f;
+            if (k_ok && row_ok[h]) {
+                if (nested) {
+                    sv[h][0] = ns[h][0];
+                    sv[h][1] = ns[h][1];
+                } else {
+                    sv[h][0] = lds_f1(st + 2048 + (2 * h) * 128 + lane * 4);
+                    sv[h][1] = two_scales ? lds_f1(st + 2048 + (2 * h + 1) * 128 + lane * 4) : sv[h][0];
+                }
+            }
+        }
+        fetch_nested(i + 1);
 
         DecodeTable tab0, tab1;
-        build_table<T, QT>(s00, tab0);
-        build_table<T, QT>(s10, tab1);
+        build_table<T, QT>(sv[0][0], tab0);
+        build_table<T, QT>(sv[1][0], tab1);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             if (hh == 1 && two_scales) {
-                build_table<T, QT>(s01, tab0);
-                build_table<T, QT>(s11, tab1);
+                build_table<T, QT>(sv[0][1], tab0);
+                build_table<T, QT>(sv[1][1], tab1);
             }
-            const uint4 qa = hh ? q01 : q00;  // row g:     32 codes = k [kb + 32 hh, +32)
-            const uint4 qb = hh ? q11 : q10;  // row g + 8
-            uint32_t ra[16], rb[16];
-            decode_word(qa.x, tab0, ra + 0);
-            decode_word(qa.y, tab0, ra + 4);
-            decode_word(qa.z, tab0, ra + 8);
-            decode_word(qa.w, tab0, ra + 12);
-            decode_word(qb.x, tab1, rb + 0);
-            decode_word(qb.y, tab1, rb + 4);
-            decode_word(qb.z, tab1, rb + 8);
-            decode_word(qb.w, tab1, rb + 12);
+            // 32 codes of row g and of row g + 8: k [kb + 32 hh, +32)
+            uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
+            if (k_ok && row_ok[0]) qa = lds_v4(st + hh * 512 + lane * 16);
+            if (k_ok && row_ok[1]) qb = lds_v4(st + (2 + hh) * 512 + lane * 16);
+            const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w};
+            const uint32_t wb[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-            for (int u = 0; u < NT; ++u) {
-                // activations of token g + 8u at the same 32 k: 16 pairs
-                const uint4* xp = reinterpret_cast<const uint4*>(arow[u] + kb);
-                uint32_t xw[16];
+            for (int w = 0; w < 4; ++w) {
+                // one packed word = 8 consecutive k = two MMAs (k-slots 2t, 2t+1, 2t+8, 2t+9 each)
+                uint32_t ra[4], rb[4];
+                decode_word(wa[w], tab0, ra);
+                decode_word(wb[w], tab1, rb);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    uint4 av = make_uint4(0, 0, 0, 0);
-                    if (tok_ok[u] && k_ok) av = __ldg(xp + 4 * hh + v);
-                    xw[4 * v + 0] = av.x;
-                    xw[4 * v + 1] = av.y;
-                    xw[4 * v + 2] = av.z;
-                    xw[4 * v + 3] = av.w;
+                for (int u = 0; u < NT; ++u) {
+                    uint4 av = make_uint4(0, 0, 0, 0);  // activations of token g + 8u at the same 8 k
+                    if (tok_ok[u] && k_ok) av = __ldg(reinterpret_cast<const uint4*>(arow[u] + kb) + 4 * hh + w);
+                    WarpMma<T>::run(c[u], ra[0], rb[0], ra[1], rb[1], av.x, av.y);
+                    WarpMma<T>::run(c[u], ra[2], rb[2], ra[3], rb[3], av.z, av.w);
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    WarpMma<T>::run(c[u], ra[2 * j], rb[2 * j], ra[2 * j + 1], rb[2 * j + 1], xw[2 * j], xw[2 * j + 1]);
             }
         }
     }
+    cp_async_wait<0>();
 
     // accumulator fragment: c0/c1 = (row g, tokens 8u + 2t, 8u + 2t+1), c2/c3 = (row g + 8, same tokens)
 #pragma unroll
@@ -183,6 +252,29 @@ __global__ void __launch_bounds__(W * 32, 2)
             out[(long long)tok * ldc + n] = DT<T>::from_f32(acc + b);
         }
     }
+}
+
+// the ring needs the dynamic shared-memory opt-in (per device and instantiation)
+template <typename T, int QT, int W, int NT>
+bool launch_mma_variant(dim3 grid, cudaStream_t stream, const T* A, const uint8_t* B, const float* absmax,
+                        const uint8_t* absmax_8bit, const float* absmax_code, const float* absmax_offset, T* out,
+                        const T* bias, int M, int N, int K, int ldc, int l2) {
+    auto kern = gemv4_mma_kernel<T, QT, W, NT>;
+    constexpr int kSmem = W * kRing * kRingStageBytes;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return false;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
+            set_last_error("gemv4_mma smem attr", cudaGetLastError());
+            return false;
+        }
+        attr_set[dev] = true;
+    }
+    kern<<<grid, W * 32, kSmem, stream>>>(A, B, absmax, absmax_8bit, absmax_code, absmax_offset, out, bias, M, N, K, ldc,
+                                          l2);
+    return true;
 }
 
 } // namespace
@@ -214,12 +306,13 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
 #define BNB200_GEMV_MMA(QT, WV)                                                                                        \
     do {                                                                                                               \
         if (M <= 8)                                                                                                    \
-            gemv4_mma_kernel<T, QT, WV, 1><<<grid, WV * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code,      \
-                                                                         absmax_offset, out, bias, M, N, K, ldc, l2); \
+            ok = launch_mma_variant<T, QT, WV, 1>(grid, stream, A, B, absmax, absmax_8bit, absmax_code,               \
+                                                  absmax_offset, out, bias, M, N, K, ldc, l2);                        \
         else                                                                                                           \
-            gemv4_mma_kernel<T, QT, WV, 2><<<grid, WV * 32, 0, stream>>>(A, B, absmax, absmax_8bit, absmax_code,      \
-                                                                         absmax_offset, out, bias, M, N, K, ldc, l2); \
+            ok = launch_mma_variant<T, QT, WV, 2>(grid, stream, A, B, absmax, absmax_8bit, absmax_code,               \
+                                                  absmax_offset, out, bias, M, N, K, ldc, l2);                        \
     } while (0)
+    bool ok = false;
     if (quant_type == kNF4) {
         if (warps == 4) BNB200_GEMV_MMA(kNF4, 4);
         else if (warps == 8) BNB200_GEMV_MMA(kNF4, 8);
@@ -230,6 +323,7 @@ bool launch_gemv4_mma(const T* A, const uint8_t* B, const float* absmax, const u
         else BNB200_GEMV_MMA(kFP4, 16);
     }
 #undef BNB200_GEMV_MMA
+    if (!ok) return false;
     BNB200_CHECK_LAUNCH("gemv4_mma");
     return true;
 }

@@ -13,31 +13,40 @@
 // rebuilt around that:
 //   * a-stage = 64 k-elements = 32 TMEM columns of decoded weights per CTA.  The ring of a-stages (TMEM
 //     A slots + the matching activation slots in shared memory) has one `full` barrier per stage on the
-//     LEADER (TMA bytes of both CTAs + the decode warps of BOTH CTAs: the peer's warps arrive remotely with a
-//     relaxed cluster-scope arrive -- a cluster-scope RELEASE costs a MEMBAR.ALL.GPU, ~1300 cycles, and there is
+//     LEADER (TMA bytes of both CTAs + the decode warps of BOTH CTAs: all of them arrive with a relaxed
+//     cluster-scope arrive -- a cluster-scope RELEASE costs a MEMBAR.ALL.GPU, ~1300 cycles, and there is
 //     no generic-proxy memory to publish, only "my tcgen05.st has completed") and one `empty` barrier per
 //     stage in each CTA (tcgen05.commit multicast).
-//   * packed codes travel in their OWN, deeper ring (128 k-elements = 8 KB per stage, 8 stages) fed by a
-//     separate producer thread, so the decode warps run ahead of the tensor core instead of starting a
-//     stage's decode only after the MMA that frees the matching TMEM slot has retired.
+//   * packed codes travel in their OWN ring (128 k-elements = 8 KB per stage, 6 stages) fed by a separate
+//     producer thread, so the decode warps run ahead of the tensor core instead of starting a stage's
+//     decode only after the MMA that frees the matching TMEM slot has retired.
 //   * 16 decode warps = 4 groups x 4 warps (one per TMEM lane quarter); group g decodes the a-stages
 //     i = g (mod 4): a thread owns one feature row and the 64 codes of the stage (= one quantisation block at
 //     the default block size, so the 16-entry table is built once per 64 weights), PRMT-decodes them in
-//     registers (decode4.cuh) and writes them with ONE tcgen05.st.32x32b.x32.
+//     registers (decode4.cuh) and writes them with two tcgen05.st.32x32b.x16.
 //   * MT = 384 tokens per tile (two N = 192 MMAs per k-step, 384 accumulator columns + 4 x 32 weight
 //     columns = the whole 512-column TMEM): a decoded weight feeds 384 MACs instead of 256, which takes
-//     the ALU pipe (the PRMT decode: ~2.9 ALU instructions per weight, 64 lanes/clk/SM) off the critical
-//     path.  MT = 256 (one N = 256 MMA, 8 stages) serves smaller token counts.
+//     the ALU pipe (the PRMT decode, 64 lanes/clk/SM) off the critical path.  MT = 256 / 128 (one MMA per
+//     k-step, 8 weight slots) serve smaller token counts.
+//   * PERSISTENT: one cluster per SM pair walks the items c, c + #clusters, ...; only the first item pays the
+//     launch, the TMEM allocation, the cluster rendezvous and the cold pipeline (~10.8 k cycles, measured).
+//     Every item restarts its rings at slot 0 (compile-time slots in the unrolled MMA loop); the mbarrier
+//     phases keep counting through a per-slot parity base (ring_base_after).
 //   * epilogue: accumulators -> registers -> +bias -> T -> a row-major [tokens][128 features] tile in the
-//     (now idle) activation ring -> ONE TMA store per decode group (and per destination: the fused all-gather of
-//     the column-sharded layer is the same bulk store into each peer GPU's buffer, asynchronous, so the NVLink
-//     writes drain while the SM already runs its next CTA).  2-byte scalar stores took 15-23 k cycles per tile.
-//   * the partial last wave is split 2 ways along K; the two splits of a tile exchange one fp32 partial
+//     TOP four activation slots -> ONE TMA bulk store per decode group (and per destination: the fused all-gather
+//     of the column-sharded layer is the same bulk store into each peer GPU's buffer, asynchronous, so the NVLink
+//     writes drain while the cluster already runs its next item).  The producers refill the other slots meanwhile
+//     and wait for `tile_free` before the staged ones; `acc_empty` lets the MMA thread restart as soon as the
+//     accumulators have been read.  2-byte scalar stores took 15-23 k cycles per tile.
+//   * the partial last round is split 2 ways along K; the two halves of a tile exchange one fp32 partial
 //     through an L2-resident workspace and the LAST ARRIVER (atomic counter, no spinning) adds the other
 //     half to its own accumulators -- a + b is commutative, so the result does not depend on who is last.
+//   * all shared memory is addressed through 32-bit shared-space addresses off one base (sm100_ptx.cuh "_a"
+//     helpers): the decode loop is issue-bound, generic pointers cost it ~90 instructions per stage.
 //
 // Warp roles (608 threads): warp 0 activation producer (TMA), warp 1 MMA issuer (leader only) + TMEM
 // allocator, warps 2..17 decode then epilogue, warp 18 code producer (TMA).
+// Measurements behind the numbers in these comments: profiles/r02_pair_trace.md.
 #include "common.cuh"
 #include "decode4.cuh"
 #include "sm100_ptx.cuh"

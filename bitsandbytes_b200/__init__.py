@@ -10,12 +10,13 @@ Layout (only what the path needs):
     autograd/          matmul_4bit / matmul (MatMul4Bit, MatMul8bitLt)
     nn/                Linear4bit, Params4bit, Linear8bitLt, Int8Params
     parallel.py        column-sharded Linear4bit over NCCL (one process per GPU)
+    optim/             optimizers with 32-bit / blockwise 8-bit state (Adam, AdamW, Lion, SGD, RMSprop, ...)
 """
 __version__ = "0.1.0"
 
 from . import cextension  # noqa: F401  (loads the native library; raises on first use if missing)
 
-_LAZY = ("functional", "nn", "autograd", "utils", "parallel", "_ops")
+_LAZY = ("functional", "nn", "autograd", "utils", "parallel", "_ops", "optim")
 
 
 def __getattr__(name):

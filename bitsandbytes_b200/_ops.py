@@ -3,7 +3,7 @@
 The schema strings are the interface HF Transformers / torch.compile trace, so they are
 the reference's (reference bitsandbytes/_ops.py:9-406) verbatim; everything else here is
 ours: one table drives the definitions, and the shape functions ("fake" kernels) are
-written once per op below.  The reference's optimizer ops (:409-510) are out of scope.
+written once per op below.  The optimizer ops (:409-510) are SURVEY.md section 8 row f-4.
 
 The only device with kernels is CUDA (``backends/cuda.py``): the reference's
 cpu/default/triton/xpu/mps/hpu fan-out collapses to the single sm_100a path and there is
@@ -38,6 +38,13 @@ SCHEMAS = {
     "quantize_blockwise": "(Tensor A, Tensor code, int blocksize) -> (Tensor, Tensor)",
     "gemv_4bit": "(Tensor A, Tensor B, int[] shapeB, Tensor absmax, Tensor code, int blocksize) -> Tensor",
     "gemv_4bit.out": "(Tensor A, Tensor B, int[] shapeB, Tensor absmax, Tensor code, int blocksize, Tensor! out) -> ()",
+    "optimizer_update_32bit": "(str optimizer_name, Tensor(a0!) g, Tensor(a1!) p, Tensor(a2!) state1, Tensor(a3!)? state2, "
+    "Tensor(a4!)? unorm_vec, float max_unorm, float param_norm, float beta1, float beta2, float beta3, float alpha, "
+    "float eps, float weight_decay, int step, float lr, float gnorm_scale, bool skip_zeros=False) -> ()",
+    "optimizer_update_8bit_blockwise": "(str optimizer_name, Tensor(a0!) g, Tensor(a1!) p, Tensor(a2!) state1, "
+    "Tensor(a3!)? state2, float beta1, float beta2, float beta3, float alpha, float eps, int step, float lr, "
+    "Tensor(a4!) qmap1, Tensor(a5!)? qmap2, Tensor(a6!) absmax1, Tensor(a7!)? absmax2, float weight_decay, "
+    "float gnorm_scale, bool skip_zeros=False) -> ()",
 }
 
 _defined = False
@@ -218,3 +225,26 @@ def _(A, B, shapeB, absmax, code, blocksize, out):
 def _(A: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
     # 1/127 as the reference spells it
     return A * stats.view(-1, 1) * 7.874015718698502e-3
+
+
+def _check_optimizer_args(g, p, state1, state2, state_dtype):
+    torch._check(g.numel() == p.numel(), lambda: f"g and p must have the same number of elements, got {g.numel()} and {p.numel()}")
+    torch._check(g.dtype in _FLOATS, lambda: f"g must be bfloat16, float16, or float32, got {g.dtype}")
+    torch._check(g.dtype == p.dtype, lambda: f"Expected all tensors to have the same dtype, got g.dtype={g.dtype}, p.dtype={p.dtype}")
+    torch._check(state1.dtype == state_dtype, lambda: f"state1 must be {state_dtype}, got {state1.dtype}")
+    if state2 is not None:
+        torch._check(state2.dtype == state_dtype, lambda: f"state2 must be {state_dtype}, got {state2.dtype}")
+
+
+@fake("optimizer_update_32bit")
+def _(optimizer_name, g, p, state1, state2, unorm_vec, max_unorm, param_norm, beta1, beta2, beta3, alpha, eps,
+      weight_decay, step, lr, gnorm_scale, skip_zeros=False):
+    _check_optimizer_args(g, p, state1, state2, torch.float32)
+
+
+@fake("optimizer_update_8bit_blockwise")
+def _(optimizer_name, g, p, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr, qmap1, qmap2, absmax1, absmax2,
+      weight_decay, gnorm_scale, skip_zeros=False):
+    _check_optimizer_args(g, p, state1, state2, torch.uint8)
+    torch._check(qmap1.dtype == absmax1.dtype == torch.float32,
+                 lambda: f"Expected qmap1 and absmax1 to be float32, got {qmap1.dtype}, {absmax1.dtype}")

@@ -508,3 +508,67 @@ def _int8_mixed_scaled_mm(A, CA, CB, SCA, SCB, outlier_cols=None, bias=None):
     subA = torch.empty(0, device=A.device, dtype=A.dtype)  # keeps torch.compile's output arity fixed
     out = torch.ops.bitsandbytes.int8_scaled_mm.default(CA, CB, SCA, SCB, bias=bias, dtype=A.dtype)
     return out, subA
+
+
+# ------------------------------------------------------------------------------------------ optimizers (section 8 f-4)
+# optimizer name -> (native id, bf16 served by the reference-named 32-bit symbol)  (reference
+# backends/cuda/ops.py:985-1066: lamb is adam with max_unorm, lars is momentum with max_unorm)
+_OPTIMIZER_ID = {"adam": 0, "lamb": 0, "momentum": 1, "lars": 1, "rmsprop": 2, "adagrad": 3, "lion": 4, "ademamix": 5}
+_OPTIMIZER_8BIT = ("adam", "momentum", "rmsprop", "adagrad", "lion", "ademamix")
+
+
+def _optional_ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@kernel("optimizer_update_32bit")
+def _optimizer_update_32bit(optimizer_name, g, p, state1, state2, unorm_vec, max_unorm, param_norm, beta1, beta2, beta3,
+                            alpha, eps, weight_decay, step, lr, gnorm_scale, skip_zeros=False):
+    """One in-place step with fp32 state (reference backends/cuda/ops.py:1069-1123, kernels csrc/kernels.cu:531-909)."""
+    if optimizer_name not in _OPTIMIZER_ID:
+        raise ValueError(f"Unsupported optimizer name: {optimizer_name}. Supported optimizers: {list(_OPTIMIZER_ID)}")
+    if g.dtype not in _DTYPE_ID:
+        raise ValueError(f"Gradient+optimizer bit data type combination not supported: grad {g.dtype}, optimizer {state1.dtype}")
+    if g.dtype != p.dtype or g.numel() != p.numel():
+        raise ValueError("optimizer_update_32bit: g and p must have the same dtype and number of elements")
+    for t in (g, p, state1, state2, unorm_vec):
+        if t is not None and not t.is_contiguous():
+            raise ValueError("optimizer_update_32bit: tensors must be contiguous")
+    with _on_device(g):
+        rc = lib.cbnb_b200_optimizer_update_32bit(_OPTIMIZER_ID[optimizer_name], _DTYPE_ID[g.dtype], g.data_ptr(),
+                                                  p.data_ptr(), state1.data_ptr(), _optional_ptr(state2),
+                                                  _optional_ptr(unorm_vec), float(max_unorm), float(param_norm),
+                                                  float(beta1), float(beta2), float(beta3), float(alpha), float(eps),
+                                                  float(weight_decay), int(step), float(lr), float(gnorm_scale),
+                                                  bool(skip_zeros), g.numel(), _stream(g))
+    lib.check("optimizer_update_32bit")
+    if rc != 0:
+        raise RuntimeError(f"optimizer_update_32bit: native call returned {rc}")
+
+
+@kernel("optimizer_update_8bit_blockwise")
+def _optimizer_update_8bit_blockwise(optimizer_name, g, p, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr, qmap1,
+                                     qmap2, absmax1, absmax2, weight_decay, gnorm_scale, skip_zeros=False):
+    """One in-place step with blockwise (256) 8-bit state (reference backends/cuda/ops.py:1126-1209, kernels
+    csrc/kernels.cu:914-1325)."""
+    if optimizer_name not in _OPTIMIZER_8BIT:
+        raise ValueError(f"Unsupported optimizer name: {optimizer_name}. Supported optimizers: {list(_OPTIMIZER_8BIT)}")
+    if g.dtype not in _DTYPE_ID:
+        raise ValueError(f"Unsupported gradient dtype: {g.dtype}. Supported dtypes: torch.float32, torch.float16, torch.bfloat16")
+    if g.dtype != p.dtype or g.numel() != p.numel():
+        raise ValueError("optimizer_update_8bit_blockwise: g and p must have the same dtype and number of elements")
+    two = optimizer_name in ("adam", "ademamix")
+    if two and (state2 is None or qmap2 is None or absmax2 is None):
+        raise ValueError(f"optimizer_update_8bit_blockwise: {optimizer_name} needs state2, qmap2 and absmax2")
+    for t in (g, p, state1, state2, qmap1, qmap2, absmax1, absmax2):
+        if t is not None and not t.is_contiguous():
+            raise ValueError("optimizer_update_8bit_blockwise: tensors must be contiguous")
+    with _on_device(g):
+        rc = lib.cbnb_b200_optimizer_update_8bit_blockwise(
+            _OPTIMIZER_ID[optimizer_name], _DTYPE_ID[g.dtype], p.data_ptr(), g.data_ptr(), state1.data_ptr(),
+            _optional_ptr(state2), float(beta1), float(beta2), float(beta3), float(alpha), float(eps), int(step), float(lr),
+            qmap1.data_ptr(), _optional_ptr(qmap2), absmax1.data_ptr(), _optional_ptr(absmax2), float(weight_decay),
+            float(gnorm_scale), bool(skip_zeros), g.numel(), _stream(g))
+    lib.check("optimizer_update_8bit_blockwise")
+    if rc != 0:
+        raise RuntimeError(f"optimizer_update_8bit_blockwise: native call returned {rc}")

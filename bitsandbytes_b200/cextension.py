@@ -81,6 +81,29 @@ def _signatures():
     sig["c_mul_fp32"] = ([_VOIDP, _VOIDP, ct.c_float, ct.c_long], None)
     sig["cget_managed_ptr"] = ([ct.c_size_t], _VOIDP)
     sig["cprefetch"] = ([_VOIDP, ct.c_size_t, _I32], None)
+    # ---- optimizers
+    _F = ct.c_float
+    # (g, p, state1, state2, unorm, max_unorm, param_norm, beta1, beta2, beta3, alpha, eps, weight_decay, step, lr,
+    #  gnorm_scale, skip_zeros, n)
+    sig32 = ([_VOIDP] * 5 + [_F] * 8 + [_I32, _F, _F, ct.c_bool, _I32], None)
+    for name, sufs in (("adam", ("fp32", "fp16", "bf16")), ("lion", ("fp32", "fp16", "bf16")),
+                       ("ademamix", ("fp32", "fp16", "bf16")), ("momentum", ("32", "16")), ("rmsprop", ("32", "16")),
+                       ("adagrad", ("32", "16"))):
+        for suf in sufs:
+            sig[f"c{name}32bit_grad_{suf}"] = sig32
+    # (p, g, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr, quantiles1, quantiles2, absmax1, absmax2,
+    #  weight_decay, gnorm_scale, skip_zeros, n)
+    sig8 = ([_VOIDP] * 4 + [_F] * 5 + [_I32, _F] + [_VOIDP] * 4 + [_F, _F, ct.c_bool, _I32], None)
+    for name in ("adam", "momentum", "rmsprop", "adagrad", "lion", "ademamix"):
+        for suf in ("fp32", "fp16", "bf16"):
+            sig[f"c{name}_8bit_blockwise_grad_{suf}"] = sig8
+    # (optimizer, dtype, g, p, state1, state2, unorm, max_unorm .. gnorm_scale, skip_zeros, n, stream) -> int
+    sig["cbnb_b200_optimizer_update_32bit"] = ([_I32, _I32] + [_VOIDP] * 5 + [_F] * 8 + [_I32, _F, _F, ct.c_bool,
+                                                ct.c_longlong, _VOIDP], _I32)
+    # (optimizer, dtype, p, g, state1, state2, beta1 .. eps, step, lr, q1, q2, absmax1, absmax2, weight_decay,
+    #  gnorm_scale, skip_zeros, n, stream) -> int
+    sig["cbnb_b200_optimizer_update_8bit_blockwise"] = ([_I32, _I32] + [_VOIDP] * 4 + [_F] * 5 + [_I32, _F] + [_VOIDP] * 4
+                                                        + [_F, _F, ct.c_bool, ct.c_longlong, _VOIDP], _I32)
     return sig
 
 

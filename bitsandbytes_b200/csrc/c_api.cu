@@ -23,6 +23,16 @@ void launch_quantize_blockwise(const float* code, const T* A, float* absmax, uin
 template <typename T, int QT>
 void launch_dequantize_blockwise(const float* code, const uint8_t* A, const float* absmax, T* out, int blocksize,
                                  long long n, cudaStream_t stream);
+// optim.cu
+bool launch_optimizer32bit(int opt, int dtype, const void* g, void* p, float* s1, float* s2, float* unorm,
+                           float max_unorm, float param_norm, float beta1, float beta2, float beta3, float alpha,
+                           float eps, float wd, int step, float lr, float gnorm_scale, bool skip_zeros, long n,
+                           cudaStream_t st);
+bool launch_optimizer8bit_blockwise(int opt, int dtype, void* p, const void* g, unsigned char* s1, unsigned char* s2,
+                                    float beta1, float beta2, float beta3, float alpha, float eps, int step, float lr,
+                                    const float* q1, const float* q2, float* a1, float* a2, float wd,
+                                    float gnorm_scale, bool skip_zeros, long n, cudaStream_t st);
+
 template <typename T>
 void launch_gemv4_simt(const T* A, const uint8_t* B, const float* absmax, const uint8_t* absmax_8bit,
                        const float* absmax_code, const float* absmax_offset, const float* lut16, int quant_type,
@@ -505,6 +515,82 @@ void cprefetch(void* ptr, size_t bytes, int device) {
     cudaError_t e = cudaMemPrefetchAsync(ptr, bytes, device, 0);
     if (e != cudaSuccess) set_last_error("cprefetch", e);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizers.  The reference-named entry points (reference
+// csrc/pythonInterface.cpp:446-520: no stream argument -> legacy default stream) and the stream-taking native pair.
+// optimizer ids: 0 adam (also lamb), 1 momentum (also lars), 2 rmsprop, 3 adagrad, 4 lion, 5 ademamix.
+// ---------------------------------------------------------------------------------------------------------------
+int cbnb_b200_optimizer_update_32bit(int optimizer, int dtype, const void* g, void* p, float* state1, float* state2,
+                                     float* unorm, float max_unorm, float param_norm, float beta1, float beta2,
+                                     float beta3, float alpha, float eps, float weight_decay, int step, float lr,
+                                     float gnorm_scale, bool skip_zeros, long long n, cudaStream_t stream) {
+    return launch_optimizer32bit(optimizer, dtype, g, p, state1, state2, unorm, max_unorm, param_norm, beta1, beta2, beta3,
+                                 alpha, eps, weight_decay, step, lr, gnorm_scale, skip_zeros, (long)n, stream)
+               ? 0
+               : 100;
+}
+
+int cbnb_b200_optimizer_update_8bit_blockwise(int optimizer, int dtype, void* p, const void* g, unsigned char* state1,
+                                              unsigned char* state2, float beta1, float beta2, float beta3, float alpha,
+                                              float eps, int step, float lr, const float* quantiles1,
+                                              const float* quantiles2, float* absmax1, float* absmax2,
+                                              float weight_decay, float gnorm_scale, bool skip_zeros, long long n,
+                                              cudaStream_t stream) {
+    return launch_optimizer8bit_blockwise(optimizer, dtype, p, g, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr,
+                                          quantiles1, quantiles2, absmax1, absmax2, weight_decay, gnorm_scale,
+                                          skip_zeros, (long)n, stream)
+               ? 0
+               : 100;
+}
+
+#define BNB200_C32(name, id, ctype, suffix, dt)                                                                        \
+    void c##name##32bit_grad_##suffix(ctype* g, ctype* p, float* state1, float* state2, float* unorm, float max_unorm,  \
+                                      float param_norm, const float beta1, const float beta2, const float beta3,        \
+                                      const float alpha, const float eps, const float weight_decay, const int step,     \
+                                      const float lr, const float gnorm_scale, bool skip_zeros, const int n) {          \
+        launch_optimizer32bit(id, dt, g, p, state1, state2, unorm, max_unorm, param_norm, beta1, beta2, beta3, alpha,  \
+                              eps, weight_decay, step, lr, gnorm_scale, skip_zeros, n, 0);                              \
+    }
+BNB200_C32(adam, 0, float, fp32, 0)
+BNB200_C32(adam, 0, __half, fp16, 1)
+BNB200_C32(adam, 0, __nv_bfloat16, bf16, 2)
+BNB200_C32(momentum, 1, float, 32, 0)
+BNB200_C32(momentum, 1, __half, 16, 1)
+BNB200_C32(rmsprop, 2, float, 32, 0)
+BNB200_C32(rmsprop, 2, __half, 16, 1)
+BNB200_C32(adagrad, 3, float, 32, 0)
+BNB200_C32(adagrad, 3, __half, 16, 1)
+BNB200_C32(lion, 4, float, fp32, 0)
+BNB200_C32(lion, 4, __half, fp16, 1)
+BNB200_C32(lion, 4, __nv_bfloat16, bf16, 2)
+BNB200_C32(ademamix, 5, float, fp32, 0)
+BNB200_C32(ademamix, 5, __half, fp16, 1)
+BNB200_C32(ademamix, 5, __nv_bfloat16, bf16, 2)
+#undef BNB200_C32
+
+#define BNB200_C8(name, id, ctype, suffix, dt)                                                                         \
+    void c##name##_8bit_blockwise_grad_##suffix(ctype* p, ctype* g, unsigned char* state1, unsigned char* state2,       \
+                                                float beta1, float beta2, float beta3, float alpha, float eps,          \
+                                                int step, float lr, float* quantiles1, float* quantiles2,               \
+                                                float* absmax1, float* absmax2, float weight_decay,                     \
+                                                const float gnorm_scale, bool skip_zeros, int n) {                      \
+        launch_optimizer8bit_blockwise(id, dt, p, g, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr,         \
+                                       quantiles1, quantiles2, absmax1, absmax2, weight_decay, gnorm_scale, skip_zeros, \
+                                       n, 0);                                                                           \
+    }
+#define BNB200_C8_ALL(name, id)                                                                                        \
+    BNB200_C8(name, id, float, fp32, 0)                                                                                \
+    BNB200_C8(name, id, __half, fp16, 1)                                                                               \
+    BNB200_C8(name, id, __nv_bfloat16, bf16, 2)
+BNB200_C8_ALL(adam, 0)
+BNB200_C8_ALL(momentum, 1)
+BNB200_C8_ALL(rmsprop, 2)
+BNB200_C8_ALL(adagrad, 3)
+BNB200_C8_ALL(lion, 4)
+BNB200_C8_ALL(ademamix, 5)
+#undef BNB200_C8_ALL
+#undef BNB200_C8
 
 } // extern "C"
 #pragma GCC visibility pop

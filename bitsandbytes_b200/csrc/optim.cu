@@ -1,0 +1,518 @@
+// optim.cu -- optimizer updates with 32-bit and 8-bit blockwise state.
+//
+// What the reference does (reference csrc/kernels.cu:531-1325, launchers csrc/ops.cu:80-210, C ABI
+// csrc/pythonInterface.cpp:68-125, 446-520):
+//   * 32-bit state: one element-wise pass over (g, p, state1[, state2]); optionally a first pass that accumulates the
+//     squared norm of the would-be update into unorm[0] for the trust-ratio clipping of LAMB / LARS (max_unorm);
+//   * 8-bit state: blocks of 256 elements; a block's state bytes are dequantised through a 256-entry code book and
+//     the block's absmax, updated in fp32, the new absmax of the block is reduced, the parameters are updated, and
+//     the state is re-quantised with the 7-step search of the blockwise quantizer (csrc/kernels.cu:221-267).
+// Both are HBM-bound element-wise kernels (12-20 bytes per element), so the B200 version is about access shape, not
+// about the tensor cores: a warp owns one 256-element block (lane l handles elements l, l + 32, ...: every load and
+// store of the warp is one contiguous segment), the block's absmax is a warp-shuffle reduction (no shared-memory
+// round trip, no __syncthreads in the loop), the two code books sit in shared memory once per CTA, and the grid is
+// persistent (a multiple of the SM count).  The 32-bit kernels are plain grid-stride loops.
+//
+// Numerics follow the reference operation by operation, including what looks accidental there, because a state
+// written by one implementation must be readable by the other:
+//   * the scaled gradient is rounded to the gradient's dtype before use (32-bit kernels), the parameter is rounded
+//     to its dtype BEFORE the decoupled weight decay multiplies it;
+//   * the 8-bit Adam step uses div.approx and sqrt.approx (the reference is compiled with --use_fast_math: this
+//     file is too, see the Makefile), a NaN / Inf gradient zeroes the element's state and skips its update;
+//   * elements past n in the last block take part in the absmax with the defaults g = 0, state1 = code1[128],
+//     state2 = code2[0];
+//   * the sign of the first state survives quantisation (code +-1 when the nearest entry has the other sign);
+//   * the 1-state RMSprop / Adagrad parameter update uses the UNSCALED gradient (csrc/kernels.cu:1271-1279).
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace bnb200 {
+
+namespace {
+
+enum OptId : int { kAdam = 0, kMomentum = 1, kRmsprop = 2, kAdagrad = 3, kLion = 4, kAdemamix = 5 };
+
+constexpr int kOptBlock = 256;  // elements per 8-bit state block (reference BLOCKSIZE_1STATE / _2STATE)
+
+__device__ __forceinline__ float sgnf(float v) { return (float)((0.0f < v) - (v < 0.0f)); }
+
+template <typename T> __device__ __forceinline__ T round_to(float v) { return DT<T>::from_f32(v); }
+template <typename T> __device__ __forceinline__ float widen(T v) { return DT<T>::to_f32(v); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 32-bit state
+// ---------------------------------------------------------------------------------------------------------------
+// first pass for max_unorm > 0: unorm[0] += sum of update^2 (reference csrc/kernels.cu:531-603, 729-804)
+template <typename T, int OPT>
+__global__ void __launch_bounds__(512) optim32_unorm_kernel(const T* g, const float* s1, const float* s2, float* unorm,
+                                                            float beta1, float beta2, float eps, int step,
+                                                            float gnorm_scale, long n) {
+    __shared__ float wsum[16];
+    const float correction1 = 1.0f / (1.0f - powf(beta1, step));
+    const float correction2 = 1.0f / (1.0f - powf(beta2, step));
+    float acc = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float gv = widen<T>(round_to<T>(gnorm_scale * widen<T>(g[i])));
+        float a = s1[i];
+        switch (OPT) {
+        case kAdam: {
+            float b = s2[i];
+            a = a * beta1 + ((1.0f - beta1) * gv);
+            b = b * beta2 + ((1.0f - beta2) * (gv * gv));
+            a *= correction1;
+            b *= correction2;
+            a = a / (sqrtf(b) + eps);
+            a *= a;
+            break;
+        }
+        case kMomentum:
+            a = (step == 1) ? gv : a * beta1 + gv;
+            a = a * a;
+            break;
+        case kLion:
+            a = a * beta2 + ((1.0f - beta2) * gv);  // (not squared: as the reference)
+            break;
+        case kRmsprop:
+            a = a * beta1 + ((1.0f - beta1) * gv * gv);
+            a = __fdividef(gv, sqrtf(a) + eps);
+            a = a * a;
+            break;
+        case kAdagrad:
+            a = a + gv * gv;
+            a = __fdividef(gv, sqrtf(a) + eps);
+            a = a * a;
+            break;
+        default:  // AdEMAMix: no trust ratio
+            a = 0.f;
+            break;
+        }
+        acc += a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(unorm, v);
+    }
+}
+
+// reference csrc/kernels.cu:605-727 (two states), 806-909 (one state)
+template <typename T, int OPT>
+__global__ void __launch_bounds__(512) optim32_kernel(const T* g, T* p, float* s1, float* s2, const float* unorm,
+                                                      float max_unorm, float param_norm, float beta1, float beta2,
+                                                      float beta3, float alpha, float eps, float weight_decay, int step,
+                                                      float lr, float gnorm_scale, bool skip_zeros, long n) {
+    constexpr bool two = OPT == kAdam || OPT == kAdemamix;
+    const float correction1 = 1.0f - powf(beta1, step);
+    const float correction2 = sqrtf(1.0f - powf(beta2, step));
+    const float step_size = -lr * correction2 / correction1;
+    float update_scale = 1.0f;
+    if (max_unorm > 0.0f) {
+        update_scale = sqrtf(unorm[0]);
+        const float cap = two ? max_unorm * param_norm : max_unorm * param_norm + eps;
+        update_scale = update_scale > cap ? cap / update_scale : 1.0f;
+    }
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        T gt = round_to<T>(gnorm_scale * widen<T>(g[i]));
+        T pt = p[i];
+        float a = s1[i];
+        if (two) {
+            float b = s2[i];
+            if (OPT == kAdemamix) {
+                float c = s1[n + i];
+                const float gv = widen<T>(gt);
+                a = (a * beta1) + ((1.0f - beta1) * gv);
+                c = (c * beta3) + ((1.0f - beta3) * gv);
+                b = (b * beta2) + ((1.0f - beta2) * gv * gv);
+                pt = round_to<T>(widen<T>(pt) -
+                                 lr * (((a / correction1) + (alpha * c)) / ((sqrtf(b) / correction2) + eps)));
+                if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
+                s1[n + i] = c;
+                s1[i] = a;
+                s2[i] = b;
+                p[i] = pt;
+            } else {
+                const float gv = widen<T>(gt);
+                if (!skip_zeros || gv != 0.0f) {
+                    a = a * beta1 + ((1.0f - beta1) * gv);
+                    b = b * beta2 + ((1.0f - beta2) * (gv * gv));
+                    pt = round_to<T>(widen<T>(pt) + (update_scale * step_size * (a / (sqrtf(b) + (eps * correction2)))));
+                    if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
+                }
+                s1[i] = a;
+                s2[i] = b;
+                p[i] = pt;
+            }
+        } else {
+            // coupled (L2) weight decay folds into the gradient -- not for Lion, which decays the parameter
+            if (weight_decay > 0.0f && OPT != kLion) gt = round_to<T>(widen<T>(gt) + (widen<T>(pt) * weight_decay));
+            const float gv = widen<T>(gt);
+            if (!skip_zeros || gv != 0.0f) {
+                switch (OPT) {
+                case kMomentum:
+                    a = (step == 1) ? gv : a * beta1 + gv;
+                    pt = round_to<T>(widen<T>(pt) + update_scale * (-lr * a));
+                    break;
+                case kLion:
+                    if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - lr * weight_decay));
+                    pt = round_to<T>(widen<T>(pt) - update_scale * (lr * sgnf(a * beta1 + ((1.0f - beta1) * gv))));
+                    a = a * beta2 + ((1.0f - beta2) * gv);
+                    break;
+                case kRmsprop:
+                    a = a * beta1 + ((1.0f - beta1) * gv * gv);
+                    pt = round_to<T>(widen<T>(pt) - update_scale * (lr * __fdividef(gv, sqrtf(a) + eps)));
+                    break;
+                case kAdagrad:
+                    a = a + gv * gv;
+                    pt = round_to<T>(widen<T>(pt) - lr * __fdividef(gv, sqrtf(a) + eps));
+                    break;
+                }
+            }
+            s1[i] = a;
+            p[i] = pt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8-bit blockwise state
+// ---------------------------------------------------------------------------------------------------------------
+// nearest entry of a sorted 256-entry code book: the 7-step search from pivot 127 and the midpoint rule of the
+// reference (csrc/kernels.cu:221-267; a value exactly on a midpoint stays with the entry the search stopped at)
+__device__ __forceinline__ int code_search(const float* __restrict__ code, float x) {
+    int pivot = 127, upper_pivot = 255, lower_pivot = 0;
+    float val = code[pivot];
+#pragma unroll
+    for (int i = 64; i > 0; i >>= 1) {
+        const bool gt = x > val;
+        lower_pivot = gt ? pivot : lower_pivot;
+        upper_pivot = gt ? upper_pivot : pivot;
+        pivot += gt ? i : -i;
+        val = code[pivot];
+    }
+    if (x > val) {
+        const float midpoint = (code[upper_pivot] + val) * 0.5f;
+        return x > midpoint ? upper_pivot : pivot;
+    }
+    const float midpoint = (code[lower_pivot] + val) * 0.5f;
+    return x < midpoint ? lower_pivot : pivot;
+}
+// (code[upper_pivot] / code[lower_pivot] equal the reference's running `upper` / `lower`: those are the values last
+// seen at the pivots; the untouched initial bounds 1.0 / -1.0 / 0.0 are code[255] / never decisive -- when the
+// search never moved right, lower_pivot == pivot == 0 and both branches return 0.)
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// state1 code with the sign of the value kept (reference csrc/kernels.cu:1118-1125)
+__device__ __forceinline__ unsigned char quant_signed(const float* __restrict__ code, float s, float absmax) {
+    int c = code_search(code, __fdividef(s, absmax));
+    if (signbit(code[c]) != signbit(s)) c += (s > 0.0f) ? 1 : -1;
+    return (unsigned char)c;
+}
+
+// reference csrc/kernels.cu:914-1150
+template <typename T, int OPT>
+__global__ void __launch_bounds__(256) optim8_2state_kernel(T* p, const T* g, unsigned char* state1, unsigned char* state2,
+                                                            float beta1, float beta2, float beta3, float alpha, float eps,
+                                                            int step, float lr, const float* qmap1, const float* qmap2,
+                                                            float* absmax1, float* absmax2, float weight_decay,
+                                                            float gnorm_scale, bool skip_zeros, long n) {
+    __shared__ float code1[256];
+    __shared__ float code2[256];
+    code1[threadIdx.x] = qmap1[threadIdx.x];
+    code2[threadIdx.x] = qmap2[threadIdx.x];
+    __syncthreads();
+    (void)skip_zeros;  // (the reference's 2-state kernel ignores it too)
+    const float correction1 = 1.0f - __powf(beta1, step);
+    const float correction2 = sqrtf(1.0f - __powf(beta2, step));
+    const float step_size = __fdividef(-lr * correction2, correction1);
+    const int lane = threadIdx.x & 31;
+    const long n_blocks = (n + kOptBlock - 1) / kOptBlock;
+    const long warps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long blk = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
+        const long base = blk * kOptBlock;
+        const float am1 = absmax1[blk], am2 = absmax2[blk];
+        const float am3 = OPT == kAdemamix ? absmax1[(n + base) / kOptBlock] : 0.f;
+        float gv[8], s1[8], s2[8], s3[8];
+        bool finite[8];
+        float m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long i = base + j * 32 + lane;
+            const bool in = i < n;
+            const T gt = in ? g[i] : round_to<T>(0.0f);
+            const int c1 = in ? state1[i] : 128;
+            const int c2 = in ? state2[i] : 0;
+            const float gf = widen<T>(gt);
+            finite[j] = !isnan(gf) && !isinf(gf);
+            if (finite[j]) {
+                s2[j] = code2[c2] * am2;
+                const float gs = gf * gnorm_scale;
+                gv[j] = gs;
+                s2[j] = (s2[j] * beta2) + (((1.0f - beta2) * gs * gs));
+                s1[j] = code1[c1] * am1;
+                s1[j] = (s1[j] * beta1) + (((1.0f - beta1) * gs));
+                if (OPT == kAdemamix) {
+                    const int c3 = in ? state1[n + i] : 128;
+                    s3[j] = code1[c3] * am3;
+                    s3[j] = (s3[j] * beta3) + (((1.0f - beta3) * gs));
+                }
+            } else {
+                gv[j] = 0.f;
+                s1[j] = s2[j] = s3[j] = 0.0f;
+            }
+            m1 = fmaxf(m1, fabsf(s1[j]));
+            m2 = fmaxf(m2, fabsf(s2[j]));
+            if (OPT == kAdemamix) m3 = fmaxf(m3, fabsf(s3[j]));
+        }
+        m1 = warp_max(m1);
+        m2 = warp_max(m2);
+        if (OPT == kAdemamix) m3 = warp_max(m3);
+        if (lane == 0) {
+            absmax1[blk] = m1;
+            absmax2[blk] = m2;
+            if (OPT == kAdemamix) absmax1[(n + base) / kOptBlock] = m3;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long i = base + j * 32 + lane;
+            if (i >= n) continue;
+            if (finite[j]) {
+                T pt = p[i];
+                if (OPT == kAdemamix)
+                    pt = round_to<T>(widen<T>(pt) - lr * (((s1[j] / correction1) + (alpha * s3[j])) /
+                                                          ((sqrtf(s2[j]) / correction2) + eps)));
+                else
+                    pt = round_to<T>(widen<T>(pt) +
+                                     ((step_size * (__fdividef(s1[j], (sqrtf(s2[j]) + (correction2 * eps)))))));
+                if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
+                p[i] = pt;
+            }
+            state1[i] = quant_signed(code1, s1[j], m1);
+            state2[i] = (unsigned char)code_search(code2, __fdividef(s2[j], m2));
+            if (OPT == kAdemamix) state1[n + i] = quant_signed(code1, s3[j], m3);
+        }
+    }
+}
+
+// reference csrc/kernels.cu:1152-1325
+template <typename T, int OPT>
+__global__ void __launch_bounds__(256) optim8_1state_kernel(T* p, const T* g, unsigned char* state1, float beta1,
+                                                            float beta2, float eps, int step, float lr,
+                                                            const float* qmap1, float* absmax1, float weight_decay,
+                                                            float gnorm_scale, bool skip_zeros, long n) {
+    __shared__ float code1[256];
+    code1[threadIdx.x] = qmap1[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long n_blocks = (n + kOptBlock - 1) / kOptBlock;
+    const long warps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long blk = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
+        const long base = blk * kOptBlock;
+        const float am1 = absmax1[blk];
+        float s1[8];
+        T gts[8], pts[8];
+        bool act[8];
+        float m1 = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long i = base + j * 32 + lane;
+            const bool in = i < n;
+            gts[j] = in ? g[i] : round_to<T>(0.0f);
+            pts[j] = in ? p[i] : round_to<T>(0.0f);
+            const int c1 = in ? state1[i] : 128;
+            float gs = widen<T>(gts[j]) * gnorm_scale;
+            act[j] = !skip_zeros || widen<T>(gts[j]) != 0.0f;
+            s1[j] = code1[c1] * am1;  // (an element skipped for a zero gradient keeps its state)
+            if (act[j]) {
+                if (weight_decay > 0.0f) {
+                    if (OPT == kLion)
+                        pts[j] = round_to<T>(widen<T>(pts[j]) * (1.0f - lr * weight_decay));
+                    else
+                        gs += widen<T>(pts[j]) * weight_decay;
+                }
+                switch (OPT) {
+                case kMomentum:
+                    s1[j] = (step == 1) ? gs : (s1[j] * beta1) + gs;
+                    break;
+                case kLion:
+                    // the gradient slot carries lr * sign(...) to the parameter update, in the gradient's dtype
+                    gts[j] = round_to<T>(lr * sgnf(s1[j] * beta1 + ((1.0f - beta1) * gs)));
+                    s1[j] = s1[j] * beta2 + ((1.0f - beta2) * gs);
+                    break;
+                case kRmsprop:
+                    s1[j] = s1[j] * beta1 + ((1.0f - beta1) * (gs * gs));
+                    break;
+                case kAdagrad:
+                    s1[j] = s1[j] + (gs * gs);
+                    break;
+                }
+            }
+            m1 = fmaxf(m1, fabsf(s1[j]));
+        }
+        m1 = warp_max(m1);
+        if (lane == 0) absmax1[blk] = m1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long i = base + j * 32 + lane;
+            if (i >= n) continue;
+            if (act[j]) {
+                T pt = pts[j];
+                switch (OPT) {
+                case kMomentum:
+                    pt = round_to<T>(widen<T>(pt) - lr * s1[j]);
+                    break;
+                case kLion:
+                    pt = round_to<T>(widen<T>(pt) - widen<T>(gts[j]));
+                    break;
+                case kRmsprop:
+                case kAdagrad:
+                    pt = round_to<T>(widen<T>(pt) - lr * (__fdividef(widen<T>(gts[j]), sqrtf(s1[j]) + eps)));
+                    break;
+                }
+                p[i] = pt;
+            } else if (weight_decay > 0.0f && OPT == kLion) {
+                p[i] = pts[j];
+            }
+            state1[i] = quant_signed(code1, s1[j], m1);
+        }
+    }
+}
+
+int grid_for(long work_items, int per_cta) {
+    long ctas = (work_items + per_cta - 1) / per_cta;
+    const long cap = 8L * device_sm_count();
+    if (ctas > cap) ctas = cap;
+    return ctas < 1 ? 1 : (int)ctas;
+}
+
+template <typename T, int OPT>
+void run32(const T* g, T* p, float* s1, float* s2, float* unorm, float max_unorm, float param_norm, float beta1,
+           float beta2, float beta3, float alpha, float eps, float weight_decay, int step, float lr, float gnorm_scale,
+           bool skip_zeros, long n, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int grid = grid_for(n, 512 * 4);
+    const bool trust = max_unorm > 0.0f && OPT != kAdemamix;
+    // Lion: the parameter update comes first, the norm of the NEW state feeds the next step (reference ops.cu:124-137)
+    if (trust && OPT != kLion) {
+        cudaMemsetAsync(unorm, 0, sizeof(float), stream);
+        optim32_unorm_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, s1, s2, unorm, beta1, beta2, eps, step, gnorm_scale, n);
+    }
+    optim32_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2, beta3,
+                                                     alpha, eps, weight_decay, step, lr, gnorm_scale, skip_zeros, n);
+    if (trust && OPT == kLion) {
+        cudaMemsetAsync(unorm, 0, sizeof(float), stream);
+        optim32_unorm_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, s1, s2, unorm, beta1, beta2, eps, step, gnorm_scale, n);
+    }
+    BNB200_CHECK_LAUNCH("optimizer32bit");
+}
+
+template <typename T, int OPT>
+void run8(T* p, const T* g, unsigned char* state1, unsigned char* state2, float beta1, float beta2, float beta3,
+          float alpha, float eps, int step, float lr, const float* qmap1, const float* qmap2, float* absmax1,
+          float* absmax2, float weight_decay, float gnorm_scale, bool skip_zeros, long n, cudaStream_t stream) {
+    if (n <= 0) return;
+    const long n_blocks = (n + kOptBlock - 1) / kOptBlock;
+    const int grid = grid_for(n_blocks, 8);
+    if (OPT == kAdam || OPT == kAdemamix)
+        optim8_2state_kernel<T, OPT><<<grid, 256, 0, stream>>>(p, g, state1, state2, beta1, beta2, beta3, alpha, eps, step,
+                                                               lr, qmap1, qmap2, absmax1, absmax2, weight_decay,
+                                                               gnorm_scale, skip_zeros, n);
+    else
+        optim8_1state_kernel<T, OPT><<<grid, 256, 0, stream>>>(p, g, state1, beta1, beta2, eps, step, lr, qmap1, absmax1,
+                                                               weight_decay, gnorm_scale, skip_zeros, n);
+    BNB200_CHECK_LAUNCH("optimizer8bit_blockwise");
+}
+
+template <typename T>
+bool dispatch32(int opt, const T* g, T* p, float* s1, float* s2, float* unorm, float max_unorm, float param_norm,
+                float beta1, float beta2, float beta3, float alpha, float eps, float wd, int step, float lr,
+                float gnorm_scale, bool skip_zeros, long n, cudaStream_t st) {
+#define BNB200_O32(ID)                                                                                                 \
+    case ID:                                                                                                           \
+        run32<T, ID>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2, beta3, alpha, eps, wd, step, lr,        \
+                     gnorm_scale, skip_zeros, n, st);                                                                  \
+        return true;
+    switch (opt) {
+        BNB200_O32(kAdam)
+        BNB200_O32(kMomentum)
+        BNB200_O32(kRmsprop)
+        BNB200_O32(kAdagrad)
+        BNB200_O32(kLion)
+        BNB200_O32(kAdemamix)
+    }
+#undef BNB200_O32
+    return false;
+}
+
+template <typename T>
+bool dispatch8(int opt, T* p, const T* g, unsigned char* s1, unsigned char* s2, float beta1, float beta2, float beta3,
+               float alpha, float eps, int step, float lr, const float* q1, const float* q2, float* a1, float* a2,
+               float wd, float gnorm_scale, bool skip_zeros, long n, cudaStream_t st) {
+#define BNB200_O8(ID)                                                                                                  \
+    case ID:                                                                                                           \
+        run8<T, ID>(p, g, s1, s2, beta1, beta2, beta3, alpha, eps, step, lr, q1, q2, a1, a2, wd, gnorm_scale,          \
+                    skip_zeros, n, st);                                                                                \
+        return true;
+    switch (opt) {
+        BNB200_O8(kAdam)
+        BNB200_O8(kMomentum)
+        BNB200_O8(kRmsprop)
+        BNB200_O8(kAdagrad)
+        BNB200_O8(kLion)
+        BNB200_O8(kAdemamix)
+    }
+#undef BNB200_O8
+    return false;
+}
+
+} // namespace
+
+// dtype: 0 = fp32, 1 = fp16, 2 = bf16 (the library's convention)
+bool launch_optimizer32bit(int opt, int dtype, const void* g, void* p, float* s1, float* s2, float* unorm,
+                           float max_unorm, float param_norm, float beta1, float beta2, float beta3, float alpha,
+                           float eps, float wd, int step, float lr, float gnorm_scale, bool skip_zeros, long n,
+                           cudaStream_t st) {
+    switch (dtype) {
+    case 0:
+        return dispatch32<float>(opt, (const float*)g, (float*)p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2,
+                                 beta3, alpha, eps, wd, step, lr, gnorm_scale, skip_zeros, n, st);
+    case 1:
+        return dispatch32<__half>(opt, (const __half*)g, (__half*)p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2,
+                                  beta3, alpha, eps, wd, step, lr, gnorm_scale, skip_zeros, n, st);
+    case 2:
+        return dispatch32<__nv_bfloat16>(opt, (const __nv_bfloat16*)g, (__nv_bfloat16*)p, s1, s2, unorm, max_unorm,
+                                         param_norm, beta1, beta2, beta3, alpha, eps, wd, step, lr, gnorm_scale,
+                                         skip_zeros, n, st);
+    }
+    return false;
+}
+
+bool launch_optimizer8bit_blockwise(int opt, int dtype, void* p, const void* g, unsigned char* s1, unsigned char* s2,
+                                    float beta1, float beta2, float beta3, float alpha, float eps, int step, float lr,
+                                    const float* q1, const float* q2, float* a1, float* a2, float wd,
+                                    float gnorm_scale, bool skip_zeros, long n, cudaStream_t st) {
+    switch (dtype) {
+    case 0:
+        return dispatch8<float>(opt, (float*)p, (const float*)g, s1, s2, beta1, beta2, beta3, alpha, eps, step, lr, q1,
+                                q2, a1, a2, wd, gnorm_scale, skip_zeros, n, st);
+    case 1:
+        return dispatch8<__half>(opt, (__half*)p, (const __half*)g, s1, s2, beta1, beta2, beta3, alpha, eps, step, lr, q1,
+                                 q2, a1, a2, wd, gnorm_scale, skip_zeros, n, st);
+    case 2:
+        return dispatch8<__nv_bfloat16>(opt, (__nv_bfloat16*)p, (const __nv_bfloat16*)g, s1, s2, beta1, beta2, beta3,
+                                        alpha, eps, step, lr, q1, q2, a1, a2, wd, gnorm_scale, skip_zeros, n, st);
+    }
+    return false;
+}
+
+} // namespace bnb200

@@ -3,9 +3,9 @@
 Same names, argument meaning and error behaviour as the reference's
 ``bitsandbytes/functional.py`` (QuantState :420-610, quantize_blockwise :613,
 dequantize_blockwise :689, get_4bit_type :772, quantize_4bit :884, dequantize_4bit :992,
-gemv_4bit :1300, int8_* :1536-1673, create_dynamic_map :296).  Paged-memory helpers,
-optimizer wrappers, the deprecated igemm family and the CPU weight-repacking helpers of
-the reference are outside the hot path and are not provided.
+gemv_4bit :1300, int8_* :1536-1673, create_dynamic_map :296, optimizer_update_32bit :1080,
+optimizer_update_8bit_blockwise :1169, the paged-memory helpers :25-160).  The deprecated igemm family and
+the CPU weight-repacking helpers of the reference are not provided.
 
 All tensor work is done by the ``bitsandbytes::`` ops whose only kernels are the sm_100a
 ones (``backends/cuda.py``); tensors must live on a CUDA device.
@@ -476,6 +476,101 @@ def is_on_gpu(tensors) -> bool:
     if len(devices) > 1:
         raise RuntimeError("Input tensors need to be on the same GPU: " + str([(t.shape, t.device) for t in on]))
     return True
+
+
+# ------------------------------------------------------------------------------------ optimizers
+def is_on_gpu_or_paged(tensors) -> bool:
+    """Like is_on_gpu, but a managed ("paged") tensor -- a CPU tensor over cudaMallocManaged memory -- is accepted."""
+    on = [t for t in tensors if t is not None and not getattr(t, "is_paged", False)]
+    return is_on_gpu(on)
+
+
+def optimizer_update_32bit(optimizer_name: str, g: Tensor, p: Tensor, state1: Tensor, beta1: float, eps: float, step: int,
+                           lr: float, state2: Optional[Tensor] = None, beta2: float = 0.0, beta3: float = 0.0,
+                           alpha: float = 0.0, weight_decay: float = 0.0, gnorm_scale: float = 1.0,
+                           unorm_vec: Optional[Tensor] = None, max_unorm: float = 0.0, skip_zeros=False) -> None:
+    """In-place optimizer step with fp32 state and fp32 / fp16 / bf16 gradients and parameters (reference
+    functional.py:1080-1166).  optimizer_name: adam, momentum, rmsprop, adagrad, lion, ademamix, lamb, lars."""
+    param_norm = 0.0
+    if max_unorm > 0.0:
+        param_norm = float(torch.norm(p.data.float()))
+    is_on_gpu_or_paged([g, p, state1, state2, unorm_vec])
+    _ops_ns.optimizer_update_32bit(optimizer_name, g, p, state1, state2, unorm_vec, max_unorm, param_norm, beta1, beta2,
+                                   beta3, alpha, eps, weight_decay, step, lr, gnorm_scale, skip_zeros)
+
+
+def optimizer_update_8bit_blockwise(optimizer_name: str, g: Tensor, p: Tensor, state1: Tensor, state2: Optional[Tensor],
+                                    beta1: float, beta2: float, beta3: float, alpha: float, eps: float, step: int,
+                                    lr: float, qmap1: Tensor, qmap2: Optional[Tensor], absmax1: Tensor,
+                                    absmax2: Optional[Tensor], weight_decay: float = 0.0, gnorm_scale: float = 1.0,
+                                    skip_zeros=False) -> None:
+    """In-place optimizer step with blockwise (256) 8-bit state (reference functional.py:1169-1213)."""
+    is_on_gpu_or_paged([p, g, state1, state2, qmap1, qmap2, absmax1, absmax2])
+    _ops_ns.optimizer_update_8bit_blockwise(optimizer_name, g, p, state1, state2, beta1, beta2, beta3, alpha, eps, step, lr,
+                                            qmap1, qmap2, absmax1, absmax2, weight_decay, gnorm_scale, skip_zeros)
+
+
+class GlobalPageManager:
+    """Registry of the managed ("paged") optimizer-state tensors (reference functional.py:25-48)."""
+
+    _instance = None
+
+    def __init__(self):
+        raise RuntimeError("Call get_instance() instead")
+
+    def initialize(self):
+        self.paged_tensors = []
+
+    @classmethod
+    def get_instance(cls):
+        if cls._instance is None:
+            cls._instance = cls.__new__(cls)
+            cls._instance.initialize()
+        return cls._instance
+
+    def prefetch_all(self, to_cpu=False):
+        for t in self.paged_tensors[::-1]:  # the first ones are used first: bring them in last
+            prefetch_tensor(t, to_cpu)
+
+
+def get_paged(*shape, dtype=torch.float32, device=None):
+    """A tensor over cudaMallocManaged memory: addressable from the host and from every GPU, migrated on demand
+    (reference functional.py:91-100).  It is a CPU tensor to PyTorch; the kernels receive its raw pointer."""
+    import numpy as np
+
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    count = 1
+    for d in shape:
+        count *= int(d)
+    num_bytes = dtype.itemsize * count
+    ptr = lib.cget_managed_ptr(num_bytes)
+    lib.check("get_paged")
+    if not ptr:
+        raise RuntimeError(f"get_paged: could not allocate {num_bytes} bytes of managed memory")
+    buf = (ct.c_uint8 * num_bytes).from_address(ptr)
+    out = torch.frombuffer(np.ctypeslib.as_array(buf), dtype=dtype, count=count).view(shape)
+    out.is_paged = True
+    out.page_deviceid = device.index
+    return out
+
+
+def prefetch_tensor(A: Tensor, to_cpu=False):
+    assert getattr(A, "is_paged", False), "Only paged tensors can be prefetched!"
+    lib.cprefetch(A.data_ptr(), A.nbytes, -1 if to_cpu else A.page_deviceid)
+    lib.check("prefetch_tensor")
+
+
+def fill(A: Tensor, value, device=None, prefetch=True):
+    """A[:] = value through the native element-wise helper (works on managed tensors; reference functional.py:142)."""
+    if A.dtype == torch.float32:
+        lib.cfill_fp32(A.data_ptr(), None, float(value), A.numel())
+    elif A.dtype == torch.uint8:
+        lib.cfill_uint8(A.data_ptr(), None, int(value), A.numel())
+    else:
+        raise NotImplementedError(f"fill: dtype {A.dtype}")
+    lib.check("fill")
+    if getattr(A, "is_paged", False):
+        torch.cuda.synchronize()
 
 
 def has_avx512bf16() -> bool:  # probed by the reference's Linear4bit; never true here (no CPU path)

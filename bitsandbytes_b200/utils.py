@@ -22,3 +22,11 @@ def unpack_tensor_to_dict(tensor_data: torch.Tensor) -> dict[str, Any]:
     """Inverse of :func:`pack_dict_to_tensor`."""
     raw = bytes(tensor_data.detach().cpu().to(torch.uint8).tolist())
     return json.loads(raw.decode("utf-8"))
+
+
+def sync_gpu(t):
+    """Block until the device of `t` is idle (reference utils.py:204-208; CUDA only here)."""
+    import torch
+
+    if t.device.type == "cuda":
+        torch.cuda.synchronize()

@@ -32,6 +32,7 @@
 #define BITSANDBYTES_B200_H
 
 #include <stddef.h>
+#include <stdbool.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -198,6 +199,23 @@ void cprefetch(void* ptr, size_t bytes, int device);
 /* exported by the reference, unused by its Python layer. */
 int cigemmlt_8(void* context, int m, int n, int k, const int8_t* A, const int8_t* B, void* C, float* row_scale, int lda, int ldb, int ldc, bnb_stream_t stream);
 int cigemmlt_8_rowscale(void* context, int m, int n, int k, const int8_t* A, const int8_t* B, void* C, float* row_scale, int lda, int ldb, int ldc, bnb_stream_t stream);
+
+/* =====================================================================
+ * 4. Optimizers
+ * ===================================================================== */
+/* Replaces reference csrc/pythonInterface.cpp:446-473 (MAKE_CFUNC32; bound in bitsandbytes/backends/cuda/ops.py:985-1031):
+ * one in-place update of p (dtype of g) with fp32 state; max_unorm > 0 first accumulates the squared update norm in
+ * unorm[0] (LAMB / LARS trust ratio).  Legacy default stream, like the reference.
+ * Full list: c{adam,lion,ademamix}32bit_grad_{fp32,fp16,bf16}, c{momentum,rmsprop,adagrad}32bit_grad_{32,16}. */
+void cadam32bit_grad_fp32(float* g, float* p, float* state1, float* state2, float* unorm, float max_unorm, float param_norm, const float beta1, const float beta2, const float beta3, const float alpha, const float eps, const float weight_decay, const int step, const float lr, const float gnorm_scale, bool skip_zeros, const int n);
+/* Replaces reference csrc/pythonInterface.cpp:475-520 (MAKE_CBLOCKWISE8; bound in backends/cuda/ops.py:1033-1066):
+ * blockwise (256) 8-bit state: state bytes + per-block absmax + 256-entry code books (quantiles).
+ * Full list: c{adam,momentum,rmsprop,adagrad,lion,ademamix}_8bit_blockwise_grad_{fp32,fp16,bf16}. */
+void cadam_8bit_blockwise_grad_fp32(float* p, float* g, unsigned char* state1, unsigned char* state2, float beta1, float beta2, float beta3, float alpha, float eps, int step, float lr, float* quantiles1, float* quantiles2, float* absmax1, float* absmax2, float weight_decay, const float gnorm_scale, bool skip_zeros, int n);
+/* The same two updates with an explicit stream, 64-bit element count, optimizer id (0 adam/lamb, 1 momentum/lars,
+ * 2 rmsprop, 3 adagrad, 4 lion, 5 ademamix) and dtype id (0 fp32, 1 fp16, 2 bf16).  Return 0, or 100 for an unknown id. */
+int cbnb_b200_optimizer_update_32bit(int optimizer, int dtype, const void* g, void* p, float* state1, float* state2, float* unorm, float max_unorm, float param_norm, float beta1, float beta2, float beta3, float alpha, float eps, float weight_decay, int step, float lr, float gnorm_scale, bool skip_zeros, long long n, bnb_stream_t stream);
+int cbnb_b200_optimizer_update_8bit_blockwise(int optimizer, int dtype, void* p, const void* g, unsigned char* state1, unsigned char* state2, float beta1, float beta2, float beta3, float alpha, float eps, int step, float lr, const float* quantiles1, const float* quantiles2, float* absmax1, float* absmax2, float weight_decay, float gnorm_scale, bool skip_zeros, long long n, bnb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import sys
 import bitsandbytes_b200 as _impl
 
 sys.modules[__name__] = _impl
-for _name in ("nn", "functional", "autograd", "utils"):
+for _name in ("nn", "functional", "autograd", "utils", "optim"):
     _sub = getattr(_impl, _name, None)
     if _sub is not None:
         sys.modules[f"{__name__}.{_name}"] = _sub

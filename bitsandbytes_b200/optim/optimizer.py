@@ -134,7 +134,8 @@ class Optimizer8bit(torch.optim.Optimizer):
             if isinstance(value, dict):
                 for k, v in value.items():
                     if k in self.non_castable_tensor_keys:
-                        if move_to_device and isinstance(v, torch.Tensor) and not getattr(v, "is_paged", False):
+                        # (also a state that was paged when it was saved: it is reloaded as a plain device tensor)
+                        if move_to_device and isinstance(v, torch.Tensor):
                             value[k] = v.to(param.device)
                     else:
                         value[k] = cast(param, v)

@@ -26,7 +26,8 @@ The default line also carries
   secondary  the other BASELINE.json configs (benchmarks/paths.py): configs[1] at M in {1,16,256} and the 11008
              shapes, configs[0] blockwise quantize/dequantize GB/s vs the HBM peak, configs[2] Linear8bitLt,
              configs[4] the Llama-3-8B replica and -- under torchrun -- configs[3] the column-sharded 70B layer.
-``--workload blockwise_c1`` / ``int8_c3`` / ``sharded70b`` / ``llama8b`` print those as stand-alone lines.
+``--workload blockwise_c1`` / ``int8_c3`` / ``sharded70b`` / ``llama8b`` print those as stand-alone lines;
+``--workload optim_f4`` times the optimizer updates of SURVEY.md section 8 row f-4 (not a BASELINE config).
 ``--no-secondary`` skips them.
 """
 import argparse
@@ -323,6 +324,10 @@ def main():
         from benchmarks.llama import run_llama8b
 
         return run_llama8b(args, rank, world, local_rank)
+    if args.workload == "optim_f4":
+        from benchmarks.optim import run_optim_f4
+
+        return run_optim_f4(args, rank, world, local_rank)
     N, K, M, qt, nested = WORKLOADS[args.workload]
 
     import torch

@@ -101,82 +101,125 @@ __global__ void __launch_bounds__(512) optim32_unorm_kernel(const T* g, const fl
     }
 }
 
-// reference csrc/kernels.cu:605-727 (two states), 806-909 (one state)
+// One element of the 32-bit update (reference csrc/kernels.cu:605-727 two states, 806-909 one state).  gt / pt are
+// the gradient and the parameter in their storage type; a, b, c the states (c: AdEMAMix's slow EMA).
+struct Opt32Args {
+    float beta1, beta2, beta3, alpha, eps, weight_decay, lr, gnorm_scale;
+    float correction1, correction2, step_size, update_scale;
+    int step;
+    bool skip_zeros;
+};
+
 template <typename T, int OPT>
+__device__ __forceinline__ void opt32_element(const Opt32Args& q, T gt, T& pt, float& a, float& b, float& c) {
+    gt = round_to<T>(q.gnorm_scale * widen<T>(gt));
+    if (OPT == kAdemamix) {
+        const float gv = widen<T>(gt);
+        a = (a * q.beta1) + ((1.0f - q.beta1) * gv);
+        c = (c * q.beta3) + ((1.0f - q.beta3) * gv);
+        b = (b * q.beta2) + ((1.0f - q.beta2) * gv * gv);
+        pt = round_to<T>(widen<T>(pt) -
+                         q.lr * (((a / q.correction1) + (q.alpha * c)) / ((sqrtf(b) / q.correction2) + q.eps)));
+        if (q.weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (q.lr * q.weight_decay)));
+    } else if (OPT == kAdam) {
+        const float gv = widen<T>(gt);
+        if (!q.skip_zeros || gv != 0.0f) {
+            a = a * q.beta1 + ((1.0f - q.beta1) * gv);
+            b = b * q.beta2 + ((1.0f - q.beta2) * (gv * gv));
+            pt = round_to<T>(widen<T>(pt) +
+                             (q.update_scale * q.step_size * (a / (sqrtf(b) + (q.eps * q.correction2)))));
+            if (q.weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (q.lr * q.weight_decay)));
+        }
+    } else {
+        // coupled (L2) weight decay folds into the gradient -- not for Lion, which decays the parameter
+        if (q.weight_decay > 0.0f && OPT != kLion) gt = round_to<T>(widen<T>(gt) + (widen<T>(pt) * q.weight_decay));
+        const float gv = widen<T>(gt);
+        if (!q.skip_zeros || gv != 0.0f) {
+            switch (OPT) {
+            case kMomentum:
+                a = (q.step == 1) ? gv : a * q.beta1 + gv;
+                pt = round_to<T>(widen<T>(pt) + q.update_scale * (-q.lr * a));
+                break;
+            case kLion:
+                if (q.weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - q.lr * q.weight_decay));
+                pt = round_to<T>(widen<T>(pt) - q.update_scale * (q.lr * sgnf(a * q.beta1 + ((1.0f - q.beta1) * gv))));
+                a = a * q.beta2 + ((1.0f - q.beta2) * gv);
+                break;
+            case kRmsprop:
+                a = a * q.beta1 + ((1.0f - q.beta1) * gv * gv);
+                pt = round_to<T>(widen<T>(pt) - q.update_scale * (q.lr * __fdividef(gv, sqrtf(a) + q.eps)));
+                break;
+            case kAdagrad:
+                a = a + gv * gv;
+                pt = round_to<T>(widen<T>(pt) - q.lr * __fdividef(gv, sqrtf(a) + q.eps));
+                break;
+            }
+        }
+    }
+}
+
+template <typename T> struct Vec4;  // four consecutive elements of T as one 8- or 16-byte access
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<__half> { using type = uint2; };
+template <> struct Vec4<__nv_bfloat16> { using type = uint2; };
+
+// VEC: four consecutive elements per thread and iteration through 8- / 16-byte accesses (every pointer 16-byte
+// aligned; the host checks), the last n % 4 elements by the first threads of CTA 0; otherwise one element per access.
+template <typename T, int OPT, bool VEC>
 __global__ void __launch_bounds__(512) optim32_kernel(const T* g, T* p, float* s1, float* s2, const float* unorm,
                                                       float max_unorm, float param_norm, float beta1, float beta2,
                                                       float beta3, float alpha, float eps, float weight_decay, int step,
                                                       float lr, float gnorm_scale, bool skip_zeros, long n) {
     constexpr bool two = OPT == kAdam || OPT == kAdemamix;
-    const float correction1 = 1.0f - powf(beta1, step);
-    const float correction2 = sqrtf(1.0f - powf(beta2, step));
-    const float step_size = -lr * correction2 / correction1;
-    float update_scale = 1.0f;
+    Opt32Args q;
+    q.beta1 = beta1, q.beta2 = beta2, q.beta3 = beta3, q.alpha = alpha, q.eps = eps, q.weight_decay = weight_decay;
+    q.lr = lr, q.gnorm_scale = gnorm_scale, q.step = step, q.skip_zeros = skip_zeros;
+    q.correction1 = 1.0f - powf(beta1, step);
+    q.correction2 = sqrtf(1.0f - powf(beta2, step));
+    q.step_size = -lr * q.correction2 / q.correction1;
+    q.update_scale = 1.0f;
     if (max_unorm > 0.0f) {
-        update_scale = sqrtf(unorm[0]);
+        const float us = sqrtf(unorm[0]);
         const float cap = two ? max_unorm * param_norm : max_unorm * param_norm + eps;
-        update_scale = update_scale > cap ? cap / update_scale : 1.0f;
+        q.update_scale = us > cap ? cap / us : 1.0f;
     }
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        T gt = round_to<T>(gnorm_scale * widen<T>(g[i]));
+    auto one = [&](long i) {
         T pt = p[i];
-        float a = s1[i];
-        if (two) {
-            float b = s2[i];
-            if (OPT == kAdemamix) {
-                float c = s1[n + i];
-                const float gv = widen<T>(gt);
-                a = (a * beta1) + ((1.0f - beta1) * gv);
-                c = (c * beta3) + ((1.0f - beta3) * gv);
-                b = (b * beta2) + ((1.0f - beta2) * gv * gv);
-                pt = round_to<T>(widen<T>(pt) -
-                                 lr * (((a / correction1) + (alpha * c)) / ((sqrtf(b) / correction2) + eps)));
-                if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
-                s1[n + i] = c;
-                s1[i] = a;
-                s2[i] = b;
-                p[i] = pt;
-            } else {
-                const float gv = widen<T>(gt);
-                if (!skip_zeros || gv != 0.0f) {
-                    a = a * beta1 + ((1.0f - beta1) * gv);
-                    b = b * beta2 + ((1.0f - beta2) * (gv * gv));
-                    pt = round_to<T>(widen<T>(pt) + (update_scale * step_size * (a / (sqrtf(b) + (eps * correction2)))));
-                    if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
-                }
-                s1[i] = a;
-                s2[i] = b;
-                p[i] = pt;
-            }
-        } else {
-            // coupled (L2) weight decay folds into the gradient -- not for Lion, which decays the parameter
-            if (weight_decay > 0.0f && OPT != kLion) gt = round_to<T>(widen<T>(gt) + (widen<T>(pt) * weight_decay));
-            const float gv = widen<T>(gt);
-            if (!skip_zeros || gv != 0.0f) {
-                switch (OPT) {
-                case kMomentum:
-                    a = (step == 1) ? gv : a * beta1 + gv;
-                    pt = round_to<T>(widen<T>(pt) + update_scale * (-lr * a));
-                    break;
-                case kLion:
-                    if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - lr * weight_decay));
-                    pt = round_to<T>(widen<T>(pt) - update_scale * (lr * sgnf(a * beta1 + ((1.0f - beta1) * gv))));
-                    a = a * beta2 + ((1.0f - beta2) * gv);
-                    break;
-                case kRmsprop:
-                    a = a * beta1 + ((1.0f - beta1) * gv * gv);
-                    pt = round_to<T>(widen<T>(pt) - update_scale * (lr * __fdividef(gv, sqrtf(a) + eps)));
-                    break;
-                case kAdagrad:
-                    a = a + gv * gv;
-                    pt = round_to<T>(widen<T>(pt) - lr * __fdividef(gv, sqrtf(a) + eps));
-                    break;
-                }
-            }
-            s1[i] = a;
-            p[i] = pt;
-        }
+        float a = s1[i], b = two ? s2[i] : 0.f, c = OPT == kAdemamix ? s1[n + i] : 0.f;
+        opt32_element<T, OPT>(q, g[i], pt, a, b, c);
+        p[i] = pt;
+        s1[i] = a;
+        if (two) s2[i] = b;
+        if (OPT == kAdemamix) s1[n + i] = c;
+    };
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long)gridDim.x * blockDim.x;
+    if (!VEC) {
+        for (long i = tid; i < n; i += nthreads) one(i);
+        return;
     }
+    using V = typename Vec4<T>::type;
+    const long n4 = n >> 2;
+    for (long v = tid; v < n4; v += nthreads) {
+        const long i = v << 2;
+        V gv4 = *reinterpret_cast<const V*>(g + i);
+        V pv4 = *reinterpret_cast<const V*>(p + i);
+        float4 a4 = *reinterpret_cast<const float4*>(s1 + i);
+        float4 b4 = two ? *reinterpret_cast<const float4*>(s2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // (AdEMAMix: s1 + n + i is 16-byte aligned only when n % 4 == 0: the host sends other sizes down the scalar path)
+        float4 c4 = OPT == kAdemamix ? *reinterpret_cast<const float4*>(s1 + n + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        T* gt = reinterpret_cast<T*>(&gv4);
+        T* pt = reinterpret_cast<T*>(&pv4);
+        float* a = reinterpret_cast<float*>(&a4);
+        float* b = reinterpret_cast<float*>(&b4);
+        float* c = reinterpret_cast<float*>(&c4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) opt32_element<T, OPT>(q, gt[k], pt[k], a[k], b[k], c[k]);
+        *reinterpret_cast<V*>(p + i) = pv4;
+        *reinterpret_cast<float4*>(s1 + i) = a4;
+        if (two) *reinterpret_cast<float4*>(s2 + i) = b4;
+        if (OPT == kAdemamix) *reinterpret_cast<float4*>(s1 + n + i) = c4;
+    }
+    if (tid < (n & 3)) one((n4 << 2) + tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -400,15 +443,24 @@ void run32(const T* g, T* p, float* s1, float* s2, float* unorm, float max_unorm
            float beta2, float beta3, float alpha, float eps, float weight_decay, int step, float lr, float gnorm_scale,
            bool skip_zeros, long n, cudaStream_t stream) {
     if (n <= 0) return;
-    const int grid = grid_for(n, 512 * 4);
+    const int grid = grid_for(n, 512 * 4 * 2);
     const bool trust = max_unorm > 0.0f && OPT != kAdemamix;
     // Lion: the parameter update comes first, the norm of the NEW state feeds the next step (reference ops.cu:124-137)
     if (trust && OPT != kLion) {
         cudaMemsetAsync(unorm, 0, sizeof(float), stream);
         optim32_unorm_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, s1, s2, unorm, beta1, beta2, eps, step, gnorm_scale, n);
     }
-    optim32_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2, beta3,
-                                                     alpha, eps, weight_decay, step, lr, gnorm_scale, skip_zeros, n);
+    auto al = [](const void* q, uintptr_t m) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & m) == 0; };
+    const bool vec = al(g, sizeof(T) * 4 - 1) && al(p, sizeof(T) * 4 - 1) && al(s1, 15) && al(s2, 15) &&
+                     (OPT != kAdemamix || (n & 3) == 0);
+    if (vec)
+        optim32_kernel<T, OPT, true><<<grid, 512, 0, stream>>>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2,
+                                                               beta3, alpha, eps, weight_decay, step, lr, gnorm_scale,
+                                                               skip_zeros, n);
+    else
+        optim32_kernel<T, OPT, false><<<grid, 512, 0, stream>>>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2,
+                                                                beta3, alpha, eps, weight_decay, step, lr, gnorm_scale,
+                                                                skip_zeros, n);
     if (trust && OPT == kLion) {
         cudaMemsetAsync(unorm, 0, sizeof(float), stream);
         optim32_unorm_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, s1, s2, unorm, beta1, beta2, eps, step, gnorm_scale, n);

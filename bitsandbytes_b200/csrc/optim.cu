@@ -6,10 +6,11 @@
 //     squared norm of the would-be update into unorm[0] for the trust-ratio clipping of LAMB / LARS (max_unorm);
 //   * 8-bit state: blocks of 256 elements; a block's state bytes are dequantised through a 256-entry code book and
 //     the block's absmax, updated in fp32, the new absmax of the block is reduced, the parameters are updated, and
-//     the state is re-quantised with the 7-step search of the blockwise quantizer (csrc/kernels.cu:221-267).
+//     the state is re-quantised with the 7-step search of the blockwise quantizer (csrc/kernels.cu:221-267; here: its
+//     bracket-table form, q8_search.cuh).
 // Both are HBM-bound element-wise kernels (12-20 bytes per element), so the B200 version is about access shape, not
-// about the tensor cores: a warp owns one 256-element block (lane l handles elements l, l + 32, ...: every load and
-// store of the warp is one contiguous segment), the block's absmax is a warp-shuffle reduction (no shared-memory
+// about the tensor cores: a warp owns one 256-element block (lane l handles the 8 consecutive elements 8 l .. 8 l + 7
+// through 8- and 16-byte accesses: every load and store of the warp is one contiguous segment), the block's absmax is a warp-shuffle reduction (no shared-memory
 // round trip, no __syncthreads in the loop), the two code books sit in shared memory once per CTA, and the grid is
 // persistent (a multiple of the SM count).  The 32-bit kernels are plain grid-stride loops.
 //
@@ -24,6 +25,7 @@
 //   * the sign of the first state survives quantisation (code +-1 when the nearest entry has the other sign);
 //   * the 1-state RMSprop / Adagrad parameter update uses the UNSCALED gradient (csrc/kernels.cu:1271-1279).
 #include "common.cuh"
+#include "q8_search.cuh"
 
 #include <cfloat>
 
@@ -225,29 +227,17 @@ __global__ void __launch_bounds__(512) optim32_kernel(const T* g, T* p, float* s
 // ---------------------------------------------------------------------------------------------------------------
 // 8-bit blockwise state
 // ---------------------------------------------------------------------------------------------------------------
-// nearest entry of a sorted 256-entry code book: the 7-step search from pivot 127 and the midpoint rule of the
-// reference (csrc/kernels.cu:221-267; a value exactly on a midpoint stays with the entry the search stopped at)
-__device__ __forceinline__ int code_search(const float* __restrict__ code, float x) {
-    int pivot = 127, upper_pivot = 255, lower_pivot = 0;
-    float val = code[pivot];
-#pragma unroll
-    for (int i = 64; i > 0; i >>= 1) {
-        const bool gt = x > val;
-        lower_pivot = gt ? pivot : lower_pivot;
-        upper_pivot = gt ? upper_pivot : pivot;
-        pivot += gt ? i : -i;
-        val = code[pivot];
-    }
-    if (x > val) {
-        const float midpoint = (code[upper_pivot] + val) * 0.5f;
-        return x > midpoint ? upper_pivot : pivot;
-    }
-    const float midpoint = (code[lower_pivot] + val) * 0.5f;
-    return x < midpoint ? lower_pivot : pivot;
-}
-// (code[upper_pivot] / code[lower_pivot] equal the reference's running `upper` / `lower`: those are the values last
-// seen at the pivots; the untouched initial bounds 1.0 / -1.0 / 0.0 are code[255] / never decisive -- when the
-// search never moved right, lower_pivot == pivot == 0 and both branches return 0.)
+// Nearest entry of a sorted 256-entry code book.  The reference walks 7 steps from pivot 127 and applies a midpoint
+// rule (csrc/kernels.cu:221-267: eight dependent shared-memory reads per value, two values per element); here the
+// bracket-table form of q8_search.cuh returns the same code (proved for every fp32 input of magnitude <= 1 + 2^-20,
+// NaN included, and any sorted code book: tools/micro/q8_lut_equiv.c) from one bracket read, a 0..3-step scan and one
+// decision-table read.  The tables are built once per (persistent) CTA.
+struct CodeBook {
+    const float* code;     // [256]
+    const float2* fin;     // [257] decision table
+    const uint32_t* br;    // [kQ8Cells] bracket table
+    __device__ __forceinline__ int search(float x) const { return (int)quantize_8bit_fast(code, fin, br, x); }
+};
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -256,10 +246,59 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // state1 code with the sign of the value kept (reference csrc/kernels.cu:1118-1125)
-__device__ __forceinline__ unsigned char quant_signed(const float* __restrict__ code, float s, float absmax) {
-    int c = code_search(code, __fdividef(s, absmax));
-    if (signbit(code[c]) != signbit(s)) c += (s > 0.0f) ? 1 : -1;
+__device__ __forceinline__ unsigned char quant_signed(const CodeBook& cb, float s, float absmax) {
+    int c = cb.search(__fdividef(s, absmax));
+    if (signbit(cb.code[c]) != signbit(s)) c += (s > 0.0f) ? 1 : -1;
     return (unsigned char)c;
+}
+
+// A lane's 8 consecutive elements of a 256-element block (element j of lane l: base + 8 l + j): one 16-byte (T = 2
+// bytes) or two 16-byte (fp32) accesses per tensor and an 8-byte access per state, when the block is whole and the
+// pointers are aligned (`vec`); element by element with the reference's padding defaults otherwise.
+template <typename T> __device__ __forceinline__ void load8(const T* src, long i0, long n, bool vec, T fill, T (&v)[8]) {
+    if (vec) {
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(src + i0);
+        } else {
+            reinterpret_cast<uint4*>(v)[0] = reinterpret_cast<const uint4*>(src + i0)[0];
+            reinterpret_cast<uint4*>(v)[1] = reinterpret_cast<const uint4*>(src + i0)[1];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (i0 + j < n) ? src[i0 + j] : fill;
+    }
+}
+template <typename T> __device__ __forceinline__ void store8(T* dst, long i0, long n, bool vec, const T (&v)[8]) {
+    if (vec) {
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(dst + i0) = *reinterpret_cast<const uint4*>(v);
+        } else {
+            reinterpret_cast<uint4*>(dst + i0)[0] = reinterpret_cast<const uint4*>(v)[0];
+            reinterpret_cast<uint4*>(dst + i0)[1] = reinterpret_cast<const uint4*>(v)[1];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j < n) dst[i0 + j] = v[j];
+    }
+}
+__device__ __forceinline__ void load8c(const unsigned char* src, long i0, long n, bool vec, unsigned char fill,
+                                       unsigned char (&v)[8]) {
+    if (vec) {
+        *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(src + i0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (i0 + j < n) ? src[i0 + j] : fill;
+    }
+}
+__device__ __forceinline__ void store8c(unsigned char* dst, long i0, long n, bool vec, const unsigned char (&v)[8]) {
+    if (vec) {
+        *reinterpret_cast<uint2*>(dst + i0) = *reinterpret_cast<const uint2*>(v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j < n) dst[i0 + j] = v[j];
+    }
 }
 
 // reference csrc/kernels.cu:914-1150
@@ -271,9 +310,19 @@ __global__ void __launch_bounds__(256) optim8_2state_kernel(T* p, const T* g, un
                                                             float gnorm_scale, bool skip_zeros, long n) {
     __shared__ float code1[256];
     __shared__ float code2[256];
+    __shared__ float2 fin1[257], fin2[257];
+    __shared__ uint32_t br1[kQ8Cells], br2[kQ8Cells];
     code1[threadIdx.x] = qmap1[threadIdx.x];
     code2[threadIdx.x] = qmap2[threadIdx.x];
     __syncthreads();
+    build_q8_bracket(code1, br1);
+    build_q8_final(code1, fin1);
+    build_q8_bracket(code2, br2);
+    build_q8_final(code2, fin2);
+    __syncthreads();
+    const CodeBook cb1{code1, fin1, br1}, cb2{code2, fin2, br2};
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(state1) | reinterpret_cast<uintptr_t>(state2)) & 7) == 0;
     (void)skip_zeros;  // (the reference's 2-state kernel ignores it too)
     const float correction1 = 1.0f - __powf(beta1, step);
     const float correction2 = sqrtf(1.0f - __powf(beta2, step));
@@ -285,32 +334,33 @@ __global__ void __launch_bounds__(256) optim8_2state_kernel(T* p, const T* g, un
         const long base = blk * kOptBlock;
         const float am1 = absmax1[blk], am2 = absmax2[blk];
         const float am3 = OPT == kAdemamix ? absmax1[(n + base) / kOptBlock] : 0.f;
-        float gv[8], s1[8], s2[8], s3[8];
+        const long i0 = base + lane * 8;
+        const bool vec = aligned && base + kOptBlock <= n;
+        alignas(16) T gts[8];
+        alignas(16) T pts[8];
+        alignas(8) unsigned char c1s[8], c2s[8], c3s[8];
+        load8<T>(g, i0, n, vec, round_to<T>(0.0f), gts);
+        load8c(state1, i0, n, vec, 128, c1s);
+        load8c(state2, i0, n, vec, 0, c2s);
+        if (OPT == kAdemamix) load8c(state1 + n, i0, n, vec && (n & 7) == 0, 128, c3s);
+        float s1[8], s2[8], s3[8];
         bool finite[8];
         float m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const long i = base + j * 32 + lane;
-            const bool in = i < n;
-            const T gt = in ? g[i] : round_to<T>(0.0f);
-            const int c1 = in ? state1[i] : 128;
-            const int c2 = in ? state2[i] : 0;
-            const float gf = widen<T>(gt);
+            const float gf = widen<T>(gts[j]);
             finite[j] = !isnan(gf) && !isinf(gf);
             if (finite[j]) {
-                s2[j] = code2[c2] * am2;
+                s2[j] = code2[c2s[j]] * am2;
                 const float gs = gf * gnorm_scale;
-                gv[j] = gs;
                 s2[j] = (s2[j] * beta2) + (((1.0f - beta2) * gs * gs));
-                s1[j] = code1[c1] * am1;
+                s1[j] = code1[c1s[j]] * am1;
                 s1[j] = (s1[j] * beta1) + (((1.0f - beta1) * gs));
                 if (OPT == kAdemamix) {
-                    const int c3 = in ? state1[n + i] : 128;
-                    s3[j] = code1[c3] * am3;
+                    s3[j] = code1[c3s[j]] * am3;
                     s3[j] = (s3[j] * beta3) + (((1.0f - beta3) * gs));
                 }
             } else {
-                gv[j] = 0.f;
                 s1[j] = s2[j] = s3[j] = 0.0f;
             }
             m1 = fmaxf(m1, fabsf(s1[j]));
@@ -325,12 +375,11 @@ __global__ void __launch_bounds__(256) optim8_2state_kernel(T* p, const T* g, un
             absmax2[blk] = m2;
             if (OPT == kAdemamix) absmax1[(n + base) / kOptBlock] = m3;
         }
+        load8<T>(p, i0, n, vec, round_to<T>(0.0f), pts);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const long i = base + j * 32 + lane;
-            if (i >= n) continue;
             if (finite[j]) {
-                T pt = p[i];
+                T pt = pts[j];
                 if (OPT == kAdemamix)
                     pt = round_to<T>(widen<T>(pt) - lr * (((s1[j] / correction1) + (alpha * s3[j])) /
                                                           ((sqrtf(s2[j]) / correction2) + eps)));
@@ -338,12 +387,16 @@ __global__ void __launch_bounds__(256) optim8_2state_kernel(T* p, const T* g, un
                     pt = round_to<T>(widen<T>(pt) +
                                      ((step_size * (__fdividef(s1[j], (sqrtf(s2[j]) + (correction2 * eps)))))));
                 if (weight_decay > 0.0f) pt = round_to<T>(widen<T>(pt) * (1.0f - (lr * weight_decay)));
-                p[i] = pt;
+                pts[j] = pt;
             }
-            state1[i] = quant_signed(code1, s1[j], m1);
-            state2[i] = (unsigned char)code_search(code2, __fdividef(s2[j], m2));
-            if (OPT == kAdemamix) state1[n + i] = quant_signed(code1, s3[j], m3);
+            c1s[j] = quant_signed(cb1, s1[j], m1);
+            c2s[j] = (unsigned char)cb2.search(__fdividef(s2[j], m2));
+            if (OPT == kAdemamix) c3s[j] = quant_signed(cb1, s3[j], m3);
         }
+        store8<T>(p, i0, n, vec, pts);
+        store8c(state1, i0, n, vec, c1s);
+        store8c(state2, i0, n, vec, c2s);
+        if (OPT == kAdemamix) store8c(state1 + n, i0, n, vec && (n & 7) == 0, c3s);
     }
 }
 
@@ -354,28 +407,38 @@ __global__ void __launch_bounds__(256) optim8_1state_kernel(T* p, const T* g, un
                                                             const float* qmap1, float* absmax1, float weight_decay,
                                                             float gnorm_scale, bool skip_zeros, long n) {
     __shared__ float code1[256];
+    __shared__ float2 fin1[257];
+    __shared__ uint32_t br1[kQ8Cells];
     code1[threadIdx.x] = qmap1[threadIdx.x];
     __syncthreads();
+    build_q8_bracket(code1, br1);
+    build_q8_final(code1, fin1);
+    __syncthreads();
+    const CodeBook cb1{code1, fin1, br1};
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(state1) & 7) == 0;
     const int lane = threadIdx.x & 31;
     const long n_blocks = (n + kOptBlock - 1) / kOptBlock;
     const long warps = (long)gridDim.x * (blockDim.x >> 5);
     for (long blk = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
         const long base = blk * kOptBlock;
         const float am1 = absmax1[blk];
+        const long i0 = base + lane * 8;
+        const bool vec = aligned && base + kOptBlock <= n;
+        alignas(16) T gts[8];
+        alignas(16) T pts[8];
+        alignas(8) unsigned char c1s[8];
+        load8<T>(g, i0, n, vec, round_to<T>(0.0f), gts);
+        load8<T>(p, i0, n, vec, round_to<T>(0.0f), pts);
+        load8c(state1, i0, n, vec, 128, c1s);
         float s1[8];
-        T gts[8], pts[8];
         bool act[8];
         float m1 = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const long i = base + j * 32 + lane;
-            const bool in = i < n;
-            gts[j] = in ? g[i] : round_to<T>(0.0f);
-            pts[j] = in ? p[i] : round_to<T>(0.0f);
-            const int c1 = in ? state1[i] : 128;
             float gs = widen<T>(gts[j]) * gnorm_scale;
             act[j] = !skip_zeros || widen<T>(gts[j]) != 0.0f;
-            s1[j] = code1[c1] * am1;  // (an element skipped for a zero gradient keeps its state)
+            s1[j] = code1[c1s[j]] * am1;  // (an element skipped for a zero gradient keeps its state)
             if (act[j]) {
                 if (weight_decay > 0.0f) {
                     if (OPT == kLion)
@@ -406,8 +469,6 @@ __global__ void __launch_bounds__(256) optim8_1state_kernel(T* p, const T* g, un
         if (lane == 0) absmax1[blk] = m1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const long i = base + j * 32 + lane;
-            if (i >= n) continue;
             if (act[j]) {
                 T pt = pts[j];
                 switch (OPT) {
@@ -422,12 +483,12 @@ __global__ void __launch_bounds__(256) optim8_1state_kernel(T* p, const T* g, un
                     pt = round_to<T>(widen<T>(pt) - lr * (__fdividef(widen<T>(gts[j]), sqrtf(s1[j]) + eps)));
                     break;
                 }
-                p[i] = pt;
-            } else if (weight_decay > 0.0f && OPT == kLion) {
-                p[i] = pts[j];
+                pts[j] = pt;
             }
-            state1[i] = quant_signed(code1, s1[j], m1);
+            c1s[j] = quant_signed(cb1, s1[j], m1);
         }
+        store8<T>(p, i0, n, vec, pts);
+        store8c(state1, i0, n, vec, c1s);
     }
 }
 
@@ -451,7 +512,9 @@ void run32(const T* g, T* p, float* s1, float* s2, float* unorm, float max_unorm
         optim32_unorm_kernel<T, OPT><<<grid, 512, 0, stream>>>(g, s1, s2, unorm, beta1, beta2, eps, step, gnorm_scale, n);
     }
     auto al = [](const void* q, uintptr_t m) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & m) == 0; };
-    const bool vec = al(g, sizeof(T) * 4 - 1) && al(p, sizeof(T) * 4 - 1) && al(s1, 15) && al(s2, 15) &&
+    // 16-bit parameters only: there the rounding to T hides how the compiler contracts an fma, and the vector kernel is
+    // bit-identical to the scalar one (and to the reference); fp32 already moves 128 bytes per warp access
+    const bool vec = sizeof(T) == 2 && al(g, sizeof(T) * 4 - 1) && al(p, sizeof(T) * 4 - 1) && al(s1, 15) && al(s2, 15) &&
                      (OPT != kAdemamix || (n & 3) == 0);
     if (vec)
         optim32_kernel<T, OPT, true><<<grid, 512, 0, stream>>>(g, p, s1, s2, unorm, max_unorm, param_norm, beta1, beta2,

@@ -405,7 +405,23 @@ def _int8_vectorwise_quant(A: torch.Tensor, threshold=0.0):
 
 @kernel("int8_double_quant")
 def _int8_double_quant(A: torch.Tensor, threshold=0.0):
+    """Row-wise and column-wise int8 codes + statistics (reference backends/cuda/ops.py:257-296).  The column half is one
+    native absmax pass and one quantise pass (`csrc/int8.cu`), bit-identical to the reference's five PyTorch kernels
+    (`tests/test_gpu_int8.py`); the PyTorch formula below remains for anything the native entry does not take."""
     q_row, row_stats, outlier_cols = torch.ops.bitsandbytes.int8_vectorwise_quant.default(A, threshold=threshold)
+    cols = A.shape[-1]
+    rows = A.numel() // cols if cols else 0
+    if A.dtype == torch.float16 and rows > 0:  # (the row half above accepts fp16 only, as the reference's does)
+        _check_sizes("int8_double_quant", A.numel())
+        A2 = A.reshape(rows, cols).contiguous()
+        q_col = torch.empty((rows, cols), device=A.device, dtype=torch.int8)
+        col_stats = torch.empty((cols,), device=A.device, dtype=torch.float32)
+        with _on_device(A):
+            rc = lib.cbnb_b200_int8_col_quant(A2.data_ptr(), q_col.data_ptr(), col_stats.data_ptr(), float(threshold), rows,
+                                              cols, _DTYPE_ID[A.dtype], _stream(A))
+        lib.check("int8_double_quant")
+        if rc == 0:
+            return q_row, q_col.view(A.shape), row_stats, col_stats, outlier_cols
     absA = A.abs().view(-1, A.shape[-1])
     mask = None
     if threshold > 0.0:

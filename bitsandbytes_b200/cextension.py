@@ -70,6 +70,8 @@ def _signatures():
     sig["cbnb_b200_int8_mixed_mm"] = ([_VOIDP] * 7 + [_I32] + [_VOIDP] + [_I32] * 4 + [_VOIDP], _I32)
     # (A, CB, SCB, cols, J, jpad, M, N, K, dtype, subA, subBT, stream)
     sig["cbnb_b200_int8_outlier_prep"] = ([_VOIDP] * 4 + [_I32] * 6 + [_VOIDP] * 3, None)
+    # (A, out, col_stats, threshold, rows, cols, dtype, stream) -> int
+    sig["cbnb_b200_int8_col_quant"] = ([_VOIDP] * 3 + [ct.c_float] + [_I32] * 3 + [_VOIDP], _I32)
     # (CA, cols, J, rows, K, stream)
     sig["cbnb_b200_int8_zero_columns"] = ([_VOIDP] * 2 + [_I32] * 3 + [_VOIDP], None)
     # (A, out, rowStats, col_flags, threshold, rows, cols, dtype, stream)

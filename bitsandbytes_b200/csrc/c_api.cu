@@ -61,6 +61,8 @@ int launch_int8_gemm(const int8_t* acts, const int8_t* weights, void* out, const
 void launch_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J, int jpad,
                               int M, int N, int K, int dtype, void* subA, void* subBT, cudaStream_t stream);
 void launch_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream);
+bool launch_int8_col_quant(const void* A, int8_t* out, float* col_stats, float threshold, int rows, int cols, int dtype,
+                           cudaStream_t stream);
 
 template <typename T, int FUNC> void launch_elementwise(T* A, const T* B, T value, long n);
 
@@ -453,6 +455,13 @@ void cbnb_b200_int8_outlier_prep(const void* A, const int8_t* CB, const float* S
 
 void cbnb_b200_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream) {
     launch_int8_zero_columns(CA, cols, J, rows, K, stream);
+}
+
+// Column-wise absmax + int8 codes of A[rows, cols] (the column half of the reference's int8_double_quant,
+// backends/cuda/ops.py:262-296, used by MatMul8bitLt.backward).  dtype 1 = fp16, 2 = bf16.  Returns 0 / 100.
+int cbnb_b200_int8_col_quant(const void* A, int8_t* out, float* col_stats, float threshold, int rows, int cols, int dtype,
+                             cudaStream_t stream) {
+    return launch_int8_col_quant(A, out, col_stats, threshold, rows, cols, dtype, stream) ? 0 : 100;
 }
 
 void cdequant_mm_int32_fp16(int* A, float* rowStats, float* colStats, __half* out, __half* bias, int numRows,

@@ -205,6 +205,83 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column-wise int8 quantisation for MatMul8bitLt.backward: the reference computes it
+// with five PyTorch kernels (backends/cuda/ops.py:262-296: abs, mask, amax over rows, masked_fill, mul / div / round /
+// cast).  Here: one pass for the column absmax (entries >= threshold excluded), one for the codes:
+//     q[r, c] = int8( rint( float( T(A[r, c] * 127) ) / col_stats[c] ) ),   outliers -> 0
+// (the product is rounded to T, as `A.mul(127.0)` on a T tensor is; the division is fp32 round-to-nearest, as the
+// T / fp32 type promotion makes it; a column without a non-outlier entry divides 0 by 0 and casts the NaN to 0).
+// A warp walks rows; a lane owns 8 consecutive columns (16-byte loads, 8-byte stores of the codes).
+template <typename T>
+__global__ void __launch_bounds__(256) int8_col_absmax_kernel(const T* __restrict__ A, float* __restrict__ col_stats,
+                                                              float threshold, int rows, int cols, int rows_per_cta) {
+    const int c0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;  // this lane's first column
+    const int r_begin = blockIdx.y * rows_per_cta + (threadIdx.x >> 5);
+    const int r_end = min(rows, (blockIdx.y + 1) * rows_per_cta);
+    if (c0 >= cols) return;
+    float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool full = c0 + 8 <= cols && (cols & 7) == 0;
+    for (int r = r_begin; r < r_end; r += 8) {
+        float v[8];
+        if (full) {
+            unpack8<T>(__ldg(reinterpret_cast<const uint4*>(A + (long long)r * cols + c0)), v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? DT<T>::to_f32(A[(long long)r * cols + c0 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = fabsf(v[j]);
+            if (!(threshold > 0.0f && a >= threshold)) m[j] = fmaxf(m[j], a);
+        }
+    }
+    // non-negative floats order like their bit patterns: an integer atomicMax combines the CTAs' partial maxima
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (c0 + j < cols && m[j] > 0.f) atomicMax(reinterpret_cast<int*>(col_stats) + c0 + j, __float_as_int(m[j]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) int8_col_quant_kernel(const T* __restrict__ A, const float* __restrict__ col_stats,
+                                                             int8_t* __restrict__ out, float threshold, int rows, int cols,
+                                                             int rows_per_cta) {
+    const int c0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
+    const int r_begin = blockIdx.y * rows_per_cta + (threadIdx.x >> 5);
+    const int r_end = min(rows, (blockIdx.y + 1) * rows_per_cta);
+    if (c0 >= cols) return;
+    const bool full = c0 + 8 <= cols && (cols & 7) == 0;
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = c0 + j < cols ? col_stats[c0 + j] : 1.f;
+    for (int r = r_begin; r < r_end; r += 8) {
+        float v[8];
+        if (full) {
+            unpack8<T>(__ldg(reinterpret_cast<const uint4*>(A + (long long)r * cols + c0)), v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? DT<T>::to_f32(A[(long long)r * cols + c0 + j]) : 0.f;
+        }
+        alignas(8) int8_t q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float x = v[j];
+            if (threshold > 0.0f && fabsf(x) >= threshold) x = 0.f;
+            x = DT<T>::to_f32(DT<T>::from_f32(__fmul_rn(x, 127.0f)));
+            const float d = __fdiv_rn(x, cs[j]);
+            q[j] = (d == d) ? (int8_t)__float2int_rn(d) : (int8_t)0;
+        }
+        if (full) {
+            *reinterpret_cast<uint2*>(out + (long long)r * cols + c0) = *reinterpret_cast<const uint2*>(q);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < cols) out[(long long)r * cols + c0 + j] = q[j];
+        }
+    }
+}
+
 } // namespace
 
 // ---------------------------------------------------------------- launch wrappers
@@ -222,6 +299,32 @@ void launch_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB,
                                                                           M, N, K, (__nv_bfloat16*)subA,
                                                                           (__nv_bfloat16*)subBT);
     BNB200_CHECK_LAUNCH("int8_outlier_prep");
+}
+
+// q_col[rows, cols] + col_stats[cols] of A[rows, cols]; dtype: 1 fp16, 2 bf16 (false: dtype not served)
+bool launch_int8_col_quant(const void* A, int8_t* out, float* col_stats, float threshold, int rows, int cols, int dtype,
+                           cudaStream_t stream) {
+    if (dtype != 1 && dtype != 2) return false;
+    if (rows <= 0 || cols <= 0) return true;
+    cudaMemsetAsync(col_stats, 0, sizeof(float) * (size_t)cols, stream);
+    const int col_ctas = (cols + 255) / 256;
+    // enough row slices to fill the machine, at least 8 rows (one per warp) each
+    int slices = (4 * device_sm_count() + col_ctas - 1) / col_ctas;
+    if (slices > (rows + 7) / 8) slices = (rows + 7) / 8;
+    if (slices < 1) slices = 1;
+    const int rows_per_cta = (((rows + slices - 1) / slices) + 7) / 8 * 8;
+    const dim3 grid(col_ctas, (rows + rows_per_cta - 1) / rows_per_cta);
+#define BNB200_COLQ(T)                                                                                                 \
+    int8_col_absmax_kernel<T><<<grid, 256, 0, stream>>>((const T*)A, col_stats, threshold, rows, cols, rows_per_cta);  \
+    int8_col_quant_kernel<T><<<grid, 256, 0, stream>>>((const T*)A, col_stats, out, threshold, rows, cols, rows_per_cta)
+    if (dtype == 1) {
+        BNB200_COLQ(__half);
+    } else {
+        BNB200_COLQ(__nv_bfloat16);
+    }
+#undef BNB200_COLQ
+    BNB200_CHECK_LAUNCH("int8_col_quant");
+    return true;
 }
 
 void launch_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, cudaStream_t stream) {

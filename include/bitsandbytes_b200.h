@@ -182,6 +182,11 @@ int cbnb_b200_int8_mixed_mm(const int8_t* CA, const int8_t* CB, const float* SCA
  * jpad columns.  cols: J int64 column indices on the device (torch.nonzero of the outlier flags). */
 void cbnb_b200_int8_outlier_prep(const void* A, const int8_t* CB, const float* SCB, const long long* cols, int J, int jpad, int M, int N, int K, int dtype, void* subA, void* subBT, bnb_stream_t stream);
 
+/* Column-wise half of int8_double_quant (reference backends/cuda/ops.py:262-296: five PyTorch kernels there):
+ * col_stats[c] = max_r |A[r,c]| over the entries below `threshold` (all entries when threshold == 0),
+ * out[r,c] = int8(rint(float(T(A[r,c] * 127)) / col_stats[c])), outliers -> 0.  dtype 1 = fp16, 2 = bf16.  Returns 0 / 100. */
+int cbnb_b200_int8_col_quant(const void* A, int8_t* out, float* col_stats, float threshold, int rows, int cols, int dtype, bnb_stream_t stream);
+
 /* CA[:, cols[j]] = 0 for the J outlier columns (reference backends/cuda/ops.py:233-236). */
 void cbnb_b200_int8_zero_columns(int8_t* CA, const long long* cols, int J, int rows, int K, bnb_stream_t stream);
 

@@ -147,3 +147,39 @@ def test_fused_scaled_mm_equals_gemm_then_dequant(M, N, K, with_bias):
                                    nat.stream())
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int16), want.view(torch.int16))
+
+
+# ------------------------------------------------------------------------------------------ column-wise quantisation
+def _reference_col_quant(A, threshold):
+    """The reference's column half of int8_double_quant, verbatim in behaviour (backends/cuda/ops.py:262-296)."""
+    absA = A.abs().view(-1, A.shape[-1])
+    mask = None
+    if threshold > 0.0:
+        mask = absA >= threshold
+        absA = absA.masked_fill(mask, 0.0)
+    col_stats = absA.amax(dim=0).float()
+    Ac = A.view(-1, A.shape[-1])
+    if mask is not None:
+        Ac = Ac.masked_fill(mask, 0.0)
+    return torch.round(Ac.mul(127.0) / col_stats.unsqueeze(0)).to(torch.int8), col_stats
+
+
+@pytest.mark.parametrize("shape", [(1, 8), (17, 40), (256, 1024), (1000, 777), (4096, 4096), (3, 5, 64)])
+@pytest.mark.parametrize("dtype", [torch.float16])  # (the op takes fp16 only, like the reference's: its row half is fp16)
+@pytest.mark.parametrize("threshold", [0.0, 3.0])
+def test_native_column_quant_is_bit_identical_to_the_reference_formula(shape, dtype, threshold):
+    import bitsandbytes_b200.functional as F
+
+    g = torch.Generator(device="cpu").manual_seed(sum(shape) + int(threshold))
+    A = (torch.randn(shape, generator=g) * 1.5).to(dtype).cuda()
+    A.view(-1, shape[-1])[:, 0] = 0  # a column without any non-zero entry: 0 / 0 -> code 0
+    if threshold > 0 and A.numel() > 64:
+        A.view(-1, shape[-1])[:, 1] = 7.0  # a column made of outliers only
+    want_q, want_stats = _reference_col_quant(A, threshold)
+    q_row, q_col, row_stats, col_stats, outlier_cols = F.int8_double_quant(A, threshold=threshold)
+    assert q_col.shape == A.shape and q_col.dtype == torch.int8 and col_stats.dtype == torch.float32
+    assert torch.equal(col_stats, want_stats)
+    assert torch.equal(q_col.view(-1, shape[-1]), want_q)
+    # the row half is the kernel the forward uses
+    rq, rs, oc = F.int8_vectorwise_quant(A, threshold=threshold)
+    assert torch.equal(q_row, rq) and torch.equal(row_stats, rs)

@@ -112,3 +112,81 @@ def test_a_step_on_a_cpu_parameter_fails_loudly():
     p.grad = torch.ones(16)
     with pytest.raises(NotImplementedError):
         bnb.optim.Adam8bit([p]).step()
+
+
+# ------------------------------------------------------------------------------------------ oracle pinned to the reference
+_GOLD = None
+
+
+def _gold():
+    global _GOLD
+    if _GOLD is None:
+        from pathlib import Path
+
+        _GOLD = np.load(Path(__file__).parent / "golden" / "reference_optim.npz")
+    return _GOLD
+
+
+_HYPER = {"adam": (1e-3, 0.9, 0.999, 0.0, 0.0, 1e-8), "momentum": (1e-2, 0.9, 0.0, 0.0, 0.0, 0.0),
+          "rmsprop": (1e-2, 0.99, 0.0, 0.0, 0.0, 1e-8), "adagrad": (1e-2, 0.0, 0.0, 0.0, 0.0, 1e-10),
+          "lion": (1e-4, 0.9, 0.99, 0.0, 0.0, 0.0), "ademamix": (1e-3, 0.9, 0.999, 0.9999, 5.0, 1e-8)}
+
+
+@pytest.mark.parametrize("name", list(_HYPER))
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_oracle_32bit_update_matches_the_reference_cpu_kernels(name, wd):
+    """oracle/optim_ref.update_32bit against outputs of the reference's own CPU kernel (tests/golden/make_golden_optim.py):
+    three steps, fp32.  Two known differences bound the tolerance: the CUDA kernels (and the oracle) form 1 - beta in
+    fp32 (1 - 0.999f = 0.00100005, 1 - 0.9999f = 0.000100017), the CPU kernel passes the doubles to PyTorch: up to 1.7e-4
+    relative on a state;
+    and with weight decay the CUDA kernel decays AFTER the update, the CPU kernel before it (lr * wd on the update)."""
+    gold = _gold()
+    lr, b1, b2, b3, alpha, eps = _HYPER[name]
+    tag = f"{name}_wd{int(wd > 0)}"
+    n = int(gold["n"])
+    p = gold[f"{tag}_p0"].copy()
+    s1 = np.zeros((2, n) if name == "ademamix" else (n,), np.float32)
+    s2 = np.zeros(n, np.float32) if name in ("adam", "ademamix") else None
+    for step in (1, 2, 3):
+        p_prev = p
+        p, s1, s2, _ = R.update_32bit(name, "fp32", gold[f"{tag}_g"][step - 1], p, s1, s2, step, lr, b1, b2, b3, alpha, eps, wd)
+        want = gold[f"{tag}_32_p{step}"]
+        upd = np.abs(want - p_prev).max()
+        np.testing.assert_allclose(p, want, rtol=0, atol=4e-7 * np.abs(want).max() + (2 * lr * wd + 4e-4) * upd,
+                                   err_msg=f"{tag} step {step}: p")
+        if not (wd > 0 and name in ("momentum", "rmsprop", "adagrad")):  # (coupled decay enters the state through p)
+            np.testing.assert_allclose(s1, gold[f"{tag}_32_s1_{step}"], rtol=3e-4, atol=1e-9, err_msg=f"{tag} step {step}: state1")
+            if s2 is not None:
+                np.testing.assert_allclose(s2, gold[f"{tag}_32_s2_{step}"], rtol=3e-4, atol=1e-12, err_msg=f"{tag}: state2")
+
+
+@pytest.mark.parametrize("name", list(_HYPER))
+def test_oracle_8bit_blockwise_update_matches_the_reference_cpu_kernel(name):
+    """One step from a random mid-training 8-bit state: parameters, new absmax and (almost all) new codes equal the
+    reference CPU kernel's -- that kernel re-quantises with an exact nearest-entry search and without the CUDA kernel's
+    sign fix, so a code may sit one entry away where a value lies on a midpoint or crosses zero."""
+    if name == "ademamix":
+        pytest.skip("the golden tensor has 1000 elements: the CUDA kernel (and the oracle) index the slow EMA's absmax at "
+                    "(n + i) / 256, which equals the CPU kernel's [2, blocks] layout only for n % 256 == 0")
+    gold = _gold()
+    lr, b1, b2, b3, alpha, eps = _HYPER[name]
+    tag = f"{name}_wd0"
+    two = name in ("adam", "ademamix")
+    a1 = gold[f"{tag}_8_a1"].reshape(-1)
+    got = R.update_8bit_blockwise(name, "fp32", gold[f"{tag}_g"][0], gold[f"{tag}_p0"], gold[f"{tag}_8_c1"],
+                                  gold[f"{tag}_8_c2"] if two else None, gold["code1"], gold["code2"], a1,
+                                  gold[f"{tag}_8_a2"] if two else None, 2, lr, b1, b2, b3, alpha, eps, 0.0)
+    want_p = gold[f"{tag}_8_p"]
+    upd = np.abs(want_p - gold[f"{tag}_p0"]).max()
+    np.testing.assert_allclose(got[0], want_p, rtol=0, atol=4e-7 * np.abs(want_p).max() + 2e-4 * upd, err_msg=f"{name}: p")
+    n = int(gold["n"])
+    if name != "ademamix":  # (n = 1000: the reference CUDA indexing of the slow EMA's absmax assumes n % 256 == 0)
+        np.testing.assert_allclose(got[3][:len(gold[f"{tag}_8_a1_out"].reshape(-1))], gold[f"{tag}_8_a1_out"].reshape(-1),
+                                   rtol=1e-4, err_msg=f"{name}: absmax1")
+        c1 = np.asarray(got[1]).reshape(-1)[:n].astype(np.int64)
+        w1 = gold[f"{tag}_8_c1_out"].reshape(-1)[:n].astype(np.int64)
+        assert np.mean(c1 == w1) > 0.97 and np.abs(c1 - w1).max() <= 1, f"{name}: state1 codes {np.mean(c1 == w1):.4f}"
+    if two:
+        np.testing.assert_allclose(got[4], gold[f"{tag}_8_a2_out"], rtol=1e-4, err_msg=f"{name}: absmax2")
+        c2, w2 = got[2].astype(np.int64), gold[f"{tag}_8_c2_out"].astype(np.int64)
+        assert np.mean(c2 == w2) > 0.97 and np.abs(c2 - w2).max() <= 1, f"{name}: state2 codes {np.mean(c2 == w2):.4f}"

@@ -87,7 +87,7 @@ static void build_final(const float* code, fin_t* fin) {
         fin[c].w = p | (o << 8) | ((p < (unsigned)c ? 1u : 0u) << 16);
     }
 }
-static fin_t g_fin[7][257];
+static fin_t g_fin[8][257];
 static int g_book = 0;
 #pragma omp threadprivate(g_book)
 
@@ -112,15 +112,20 @@ static int cmpf(const void* a, const void* b) {
 
 int main(void) {
     build_structure();
-    static float books[7][256];
-    static uint32_t br[7][Q8_CELLS];
+    static float books[8][256];
+    static uint32_t br[8][Q8_CELLS];
     static const float dynamic_map[256] = {
 #include "q8_dynamic_map.inc"
     };
-    const char* names[7] = {"dynamic-like (log spaced, signed)", "linear signed", "unsigned with zero padding",
+    static const float udynamic_map[256] = {
+#include "q8_udynamic_map.inc"
+    };
+    const char* names[8] = {"dynamic-like (log spaced, signed)", "linear signed", "unsigned with zero padding",
                             "4-bit values zero-padded to 256", "random sorted with duplicates",
-                            "create_dynamic_map() (the default 8-bit code)", "tiny magnitudes + a negative zero"};
+                            "create_dynamic_map() (the default 8-bit code)", "tiny magnitudes + a negative zero",
+                            "create_dynamic_map(signed=False) (second optimizer state)"};
     memcpy(books[5], dynamic_map, sizeof(dynamic_map));
+    memcpy(books[7], udynamic_map, sizeof(udynamic_map));
     for (int i = 0; i < 127; ++i) {
         float v = powf(10.0f, -7.0f * (float)(126 - i) / 126.0f);
         books[0][129 + i] = v;
@@ -141,11 +146,11 @@ int main(void) {
     books[6][0] = -1.0f; books[6][1] = -0.5f; books[6][254] = 0.5f; books[6][255] = 1.0f;
     books[6][100] = -1e-42f; books[6][101] = -0.0f; books[6][102] = 0.0f; books[6][103] = 1e-42f;
     qsort(books[6], 256, sizeof(float), cmpf);
-    for (int b = 0; b < 7; ++b) { build_bracket(books[b], br[b]); build_final(books[b], g_fin[b]); }
+    for (int b = 0; b < 8; ++b) { build_bracket(books[b], br[b]); build_final(books[b], g_fin[b]); }
 
     const float bound = 1.0f + 9.5367431640625e-07f; /* 1 + 2^-20 */
     int bad_total = 0;
-    for (int b = 0; b < 7; ++b) {
+    for (int b = 0; b < 8; ++b) {
         long long bad = 0, checked = 0;
 #pragma omp parallel for schedule(static) reduction(+ : bad, checked)
         for (long long bits = 0; bits < (1LL << 32); ++bits) {

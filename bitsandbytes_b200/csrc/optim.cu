@@ -232,36 +232,14 @@ __global__ void __launch_bounds__(512) optim32_kernel(const T* g, T* p, float* s
 // bracket-table form of q8_search.cuh returns the same code (proved for every fp32 input of magnitude <= 1 + 2^-20,
 // NaN included, and any sorted code book: tools/micro/q8_lut_equiv.c) from one bracket read, a 0..3-step scan and one
 // decision-table read.  The tables are built once per (persistent) CTA.
-// the reference's own walk (csrc/kernels.cu:221-267), for inputs outside the domain of the proof
-__device__ __noinline__ int code_walk(const float* __restrict__ code, float x) {
-    int pivot = 127, upper_pivot = 255, lower_pivot = 0;
-    float val = code[pivot];
-#pragma unroll
-    for (int i = 64; i > 0; i >>= 1) {
-        const bool gt = x > val;
-        lower_pivot = gt ? pivot : lower_pivot;
-        upper_pivot = gt ? upper_pivot : pivot;
-        pivot += gt ? i : -i;
-        val = code[pivot];
-    }
-    if (x > val) {
-        const float midpoint = (code[upper_pivot] + val) * 0.5f;
-        return x > midpoint ? upper_pivot : pivot;
-    }
-    const float midpoint = (code[lower_pivot] + val) * 0.5f;
-    return x < midpoint ? lower_pivot : pivot;
-}
-
 struct CodeBook {
     const float* code;     // [256]
     const float2* fin;     // [257] decision table
     const uint32_t* br;    // [kQ8Cells] bracket table
-    __device__ __forceinline__ int search(float x) const {
-        // |x| = |state / absmax| <= 1 up to the 2 ulp of div.approx -- unless the block's absmax is denormal and
-        // flushed to zero (x = +-Inf): out of the proved domain, take the walk
-        if (fabsf(x) > 1.0000009f) return code_walk(code, x);
-        return (int)quantize_8bit_fast(code, fin, br, x);
-    }
+    // Domain of the proof: |x| <= 1 + 2^-20, or NaN.  x = div.approx.ftz(state, absmax) with |state| <= absmax, so
+    // |x| <= 1 up to 2 ulp; a denormal absmax is flushed to zero TOGETHER with the (then also denormal) state: 0 / 0 =
+    // NaN, never an infinity.
+    __device__ __forceinline__ int search(float x) const { return (int)quantize_8bit_fast(code, fin, br, x); }
 };
 
 __device__ __forceinline__ float warp_max(float v) {
